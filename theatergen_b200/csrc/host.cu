@@ -1,0 +1,76 @@
+// Host-side plumbing: error strings, launch counter, TMA descriptor encoding.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace tg {
+
+static thread_local char g_err[512] = "";
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+      return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                 uint32_t box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * 2) % 16 == 0,
+           "tmap2d: base/pitch must be 16-byte aligned (base=%p ld=%llu)", base, (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu box=%ux%u) -> %d",
+           (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols, (int)r);
+  return 0;
+}
+
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
+                   uint32_t bh, uint32_t bw) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (C * 2) % 16 == 0, "tmap nhwc: alignment");
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, bw, bh, bb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc B=%llu H=%llu W=%llu C=%llu box=%u,%u,%u) -> %d",
+           (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, bb, bh, bw,
+           (int)r);
+  return 0;
+}
+
+}  // namespace tg
