@@ -51,6 +51,81 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
                const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, float out_scale,
                tg_half* out, int ldc, void* stream);
 
+/* out = [SiLU](GroupNorm32([x1|x2])) for channels-last x1 [B,HW,C1], x2 [B,HW,C2] (x2 NULL when C2 == 0).
+ * The up-path torch.cat([hidden, skip], 1) (ip_adapter/unet_2d_blocks.py:2210-2212, 2318-2320) is folded in.
+ * workspace: >= B*64*32*2 floats.  Replaces nn.GroupNorm(+SiLU) of diffusers ResnetBlock2D (eps 1e-5),
+ * Transformer2DModel.norm (ip_adapter/transformer_2d.py:288, eps 1e-6), conv_norm_out
+ * (ip_adapter/unet_2d_condition.py:1117-1119). */
+int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
+                 const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream);
+
+/* row-wise LayerNorm (ip_adapter/attention.py:198,226,238; resampler.py:16,43-44,100; ip_adapter.py:39) */
+int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* beta, float eps, tg_half* out,
+                 int ldo, int M, int C, void* stream);
+
+/* Flash attention: O[b,n,h*d:(h+1)*d] = softmax(scale Q K^T) V per (b,h).  Q/K/V/O are token-major with row
+ * pitches ld* (elements) and head h at column offset h*d (pass pointers into a fused QKV buffer).
+ * d in {40,64,80,160}.  Replaces AttnProcessor.__call__ (ip_adapter/attention_processor.py:343-356) and
+ * PerceiverAttention's softmax(QK^T)V (ip_adapter/resampler.py:65-74). */
+int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
+                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, void* stream);
+
+/* IP-Adapter decoupled cross attention (IPAttnProcessor.__call__, ip_adapter/attention_processor.py:478-516):
+ *   O = softmax(scale Q Kt^T + add_mask) Vt + ip_scale[b] * softmax(scale Q Ki^T) Vi
+ * Kt/Vt/Ki/Vi point into a K/V projection buffer with (n_text + n_ip) rows per batch element and row pitch
+ * ldkv; text keys are rows [0,n_text), image-token keys rows [n_text, n_text+n_ip).  n_text <= 80, n_ip <= 16
+ * (n_ip == 0: plain AttnProcessor cross attention).  ip_scale: device float[B] (NULL = 1.0): the reference's
+ * python attribute `IPAttnProcessor.scale`, per sample so characters with different scales can share a batch.
+ * add_mask: device fp16 [B, n_text] additive mask or NULL.  probs: optional capture of the text
+ * probabilities, fp16 [B - probs_b0, heads, Nq, n_text] (save_attn_to_dict, :532-549; probs_b0 = B/2 is
+ * return_cond_ca_only). */
+int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg_half* Vt, const tg_half* Ki,
+                          const tg_half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
+                          const tg_half* add_mask, tg_half* O, int ldo, tg_half* probs, int probs_b0, int B,
+                          int heads, int Nq, int d, float scale, void* stream);
+
+/* layout / small ops of the UNet forward (ip_adapter/unet_2d_condition.py:897-902, 999, 1044-1053, 1117-1120;
+ * diffusers Upsample2D / Downsample2D) */
+int tg_upsample2x(const tg_half* x, int B, int H, int W, int C, tg_half* y, void* stream);
+int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, void* stream);
+int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_half* y_nhwc, int B, int H, int W,
+               int Cout, void* stream);
+int tg_conv_out(const tg_half* x_nhwc, const tg_half* w, const tg_half* bias, tg_half* y_nchw, int B, int H,
+                int W, int C, void* stream);
+int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream);
+int tg_add_inplace(tg_half* y, const tg_half* x, long long n, void* stream);
+int tg_nchw_to_nhwc(const tg_half* x, tg_half* y, int B, int C, int HW, void* stream);
+int tg_duplicate_latents(const tg_half* lat, tg_half* out, int n, void* stream);
+
+/* One launch per denoise step: classifier-free guidance + DDIM update (+ masked latent composite).
+ *   eps [2K,C,H,W] (rows [0,K) unconditional), latents [K,C,H,W] in/out, coef_dev = device float[5]
+ *   {guidance_scale, sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)}; frozen [K,C,H,W] and mask [H,W]
+ *   may be NULL (stage 1); latents_copy (nullable) receives a second copy (the latents_all trace).
+ * Replaces models/pipelines.py:441-447 and :820-834 + diffusers DDIMScheduler.step. */
+int tg_cfg_ddim_composite(const tg_half* eps, tg_half* latents, const float* coef_dev, const tg_half* frozen,
+                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, void* stream);
+
+/* Cross-attention guidance energy, utils/guidance.py:244-286 (compute_ca_lossv3) with :91-148 (top-k box
+ * energy) and :150-242 (reference-attention transfer).  All descriptor arrays are HOST memory and are passed
+ * to the kernel by value (graph capturable).
+ *   maps[k]   device fp16 [heads, map_hw[k], n_tok]   (cond half of the captured probabilities)
+ *   dmaps[k]  nullable device fp16, same shape, caller-zeroed: receives d(grad_scale*energy)/d(map)
+ *   boxes     [n_box][4] normalised x0,y0,x1,y1 (python floats); box_obj[n_box] object index of each box
+ *   items     n_items x {key, obj, tok, weight}: one top-k term; weight = 1/(n_tok_of_obj * n_obj * n_keys)
+ *   ref_items n_ref x {key, box, tok, ref, weight}: one transfer term against ref_maps[ref] [heads, map_hw]
+ *   loss_out  device float; workspace >= (n_items + n_ref) floats */
+typedef struct {
+  unsigned char key, obj, box, ref;
+  int tok;
+  float weight;
+} tg_guidance_item;
+int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const int* map_hw, int n_keys,
+                       int heads, int n_tok, const double* boxes, const int* box_obj, int n_box,
+                       const tg_guidance_item* items, int n_items, const tg_guidance_item* ref_items,
+                       const tg_half* const* ref_maps, int n_ref_items, float fg_top_p, float bg_top_p,
+                       float fg_weight, float bg_weight, float grad_scale, float ref_eps, float* loss_out,
+                       float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,177 @@
+"""GPU parity of attention / norm / layout / step kernels against fp32 torch restatements of the same op.
+(The whole-path parity against oracle/ lives in test_unet_gpu.py.)"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).half().cuda()
+
+
+def _close(got, ref, atol, rtol, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    assert bool((err <= tol).all()), f"{what} max err {err.max().item():.4e}, worst excess {(err - tol).max().item():.3e}"
+
+
+@pytest.mark.parametrize("B,N,C", [(2, 4096, 320), (2, 1024, 640), (2, 256, 1280), (2, 64, 1280), (4, 273, 768)])
+def test_self_attention(B, N, C):
+    from theatergen_b200 import ops
+    heads = 12 if C == 768 else 8
+    d = C // heads
+    qkv = _rand((B * N, 3 * C), 1)
+    out = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, heads)
+    q, k, v = [t.float().reshape(B, N, heads, d).transpose(1, 2) for t in (qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:])]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, C)
+    _close(out, ref, 2e-3, 1e-2, "self-attn")
+
+
+def test_self_attention_cross_lengths():
+    """Nq != Nk (the resampler: 16 queries over 273 keys) and sharper logits."""
+    from theatergen_b200 import ops
+    B, Nq, Nk, heads, d = 2, 16, 273, 12, 64
+    q, k, v = _rand((B * Nq, heads * d), 1, 2.0), _rand((B * Nk, heads * d), 2, 2.0), _rand((B * Nk, heads * d), 3)
+    out = ops.attention(q, k, v, B, heads)
+    qq = q.float().reshape(B, Nq, heads, d).transpose(1, 2)
+    kk = k.float().reshape(B, Nk, heads, d).transpose(1, 2)
+    vv = v.float().reshape(B, Nk, heads, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * Nq, heads * d)
+    _close(out, ref, 2e-3, 1e-2, "cross-length attn")
+
+
+@pytest.mark.parametrize("B,N,C,n_ip", [(2, 4096, 320, 4), (2, 1024, 640, 4), (4, 256, 1280, 4), (2, 64, 1280, 16),
+                                        (2, 256, 1280, 0)])
+def test_cross_attention_ip(B, N, C, n_ip):
+    from theatergen_b200 import ops
+    heads, n_text = 8, 77
+    d = C // heads
+    T = n_text + n_ip
+    q = _rand((B * N, C), 1)
+    kv = _rand((B * T, 4 * C), 2)
+    scale = torch.tensor([0.0, 0.4, 1.0, 0.1][:B] if B <= 4 else [0.4] * B, dtype=torch.float32, device="cuda")
+    probs = torch.zeros((B // 2, heads, N, n_text), dtype=torch.float16, device="cuda")
+    out = ops.attention_cross_ip(q, kv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:3 * C] if n_ip else None,
+                                 kv[:, 3 * C:] if n_ip else None, B, heads, n_text, n_ip, ip_scale=scale, probs=probs,
+                                 probs_b0=B // 2)
+    qq = q.float().reshape(B, N, heads, d).transpose(1, 2)
+    kvb = kv.float().reshape(B, T, 4, heads, d)
+    kt, vt = kvb[:, :n_text, 0].transpose(1, 2), kvb[:, :n_text, 1].transpose(1, 2)
+    p = torch.softmax(qq @ kt.transpose(-1, -2) * d ** -0.5, -1)
+    ref = p @ vt
+    if n_ip:
+        ki, vi = kvb[:, n_text:, 2].transpose(1, 2), kvb[:, n_text:, 3].transpose(1, 2)
+        pi = torch.softmax(qq @ ki.transpose(-1, -2) * d ** -0.5, -1)
+        ref = ref + scale.view(B, 1, 1, 1) * (pi @ vi)
+    ref = ref.transpose(1, 2).reshape(B * N, C)
+    _close(out, ref, 3e-3, 1e-2, "cross-attn")
+    _close(probs, p[B // 2:], 1e-3, 1e-2, "captured probs")
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu", [(2, 4096, 320, 0, True), (2, 4096, 640, 320, True),
+                                             (2, 256, 1280, 640, True), (2, 64, 1280, 1280, True),
+                                             (2, 1024, 640, 0, False)])
+def test_groupnorm(B, HW, C1, C2, silu):
+    from theatergen_b200 import ops
+    x1 = _rand((B, HW, C1), 1) + 0.5
+    x2 = _rand((B, HW, C2), 2, 2.0) if C2 else None
+    C = C1 + C2
+    gamma, beta = _rand((C,), 3) * 0.1 + 1, _rand((C,), 4, 0.1)
+    out = ops.groupnorm(x1, gamma, beta, 1e-5, x2=x2, silu=silu)
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.group_norm(x.float().transpose(1, 2), 32, gamma.float(), beta.float(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    _close(out, ref.transpose(1, 2), 4e-3, 4e-3, "groupnorm")
+
+
+@pytest.mark.parametrize("M,C", [(8192, 320), (2048, 640), (512, 1280), (273, 768), (5, 768)])
+def test_layernorm(M, C):
+    from theatergen_b200 import ops
+    x = _rand((M, C), 1, 3.0) + 1.0
+    gamma, beta = _rand((C,), 3) * 0.1 + 1, _rand((C,), 4, 0.1)
+    out = ops.layernorm(x, gamma, beta)
+    _close(out, F.layer_norm(x.float(), (C,), gamma.float(), beta.float(), 1e-5), 3e-3, 3e-3, "layernorm")
+
+
+def test_layout_kernels():
+    from theatergen_b200 import ops
+    x = _rand((2, 16, 16, 640), 1)
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    a = ops.im2col_s2(x)
+    unf = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L] (c-major, tap-minor)
+    unf = unf.reshape(2, 640, 9, 64).permute(0, 3, 2, 1).reshape(2 * 64, 9 * 640)
+    assert torch.equal(a.float(), unf)
+    n = _rand((2, 320, 8, 8), 2)
+    assert torch.equal(ops.nchw_to_nhwc(n), n.permute(0, 2, 3, 1).contiguous())
+    y = _rand((1000,), 3)
+    y0 = y.clone()
+    ops.add_inplace(y, y0)
+    assert torch.equal(y, y0 + y0)
+
+
+def test_downsample_conv_via_im2col():
+    from theatergen_b200 import ops
+    from theatergen_b200.weights import pack_conv3x3
+    B, H, W, C = 2, 32, 32, 640
+    x = _rand((B, H, W, C), 1)
+    w = _rand((C, C, 3, 3), 2, (9 * C) ** -0.5)
+    bias = _rand((C,), 3)
+    out = ops.gemm(ops.im2col_s2(x), pack_conv3x3(w).reshape(C, 9 * C), bias)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias.float(), stride=2, padding=1)
+    _close(out.reshape(B, H // 2, W // 2, C), ref.permute(0, 2, 3, 1), 3e-3, 3e-3, "downsample")
+
+
+def test_conv_in_out():
+    from theatergen_b200 import ops
+    from theatergen_b200.weights import pack_conv3x3
+    x = _rand((2, 4, 64, 64), 1)
+    w, b = _rand((320, 4, 3, 3), 2, 1 / 6), _rand((320,), 3, 0.1)
+    out = ops.conv_in(x, w, b)
+    ref = F.conv2d(x.float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-3, 2e-3, "conv_in")
+    h = _rand((2, 64, 64, 320), 4)
+    w2, b2 = _rand((4, 320, 3, 3), 5, (2880) ** -0.5), _rand((4,), 6, 0.1)
+    out2 = ops.conv_out(h, pack_conv3x3(w2), b2)
+    ref2 = F.conv2d(h.float().permute(0, 3, 1, 2), w2.float(), b2.float(), padding=1)
+    _close(out2, ref2, 2e-3, 2e-3, "conv_out")
+
+
+def test_timestep_embedding():
+    from theatergen_b200 import ops
+    t = torch.tensor([981.0, 981.0, 1.0, 501.0], device="cuda")
+    out = ops.timestep_embedding(t)
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    e = t[:, None] * f[None]
+    ref = torch.cat([torch.cos(e), torch.sin(e)], -1)
+    _close(out, ref, 2e-3, 0, "timestep embedding")
+
+
+def test_cfg_ddim_composite():
+    from theatergen_b200 import ops
+    K = 3
+    eps, lat = _rand((2 * K, 4, 64, 64), 1), _rand((K, 4, 64, 64), 2)
+    frozen, mask = _rand((K, 4, 64, 64), 3), (torch.rand(64, 64) > 0.5).half().cuda()
+    a_t, a_p, g = 0.3, 0.45, 7.5
+    coef = torch.tensor([g, a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5], device="cuda")
+    e = eps[:K].float() + g * (eps[K:].float() - eps[:K].float())
+    x0 = (lat.float() - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+    ref = a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * e
+    l1, trace = lat.clone(), torch.zeros_like(lat)
+    ops.cfg_ddim_composite(eps, l1, coef, latents_copy=trace)
+    _close(l1, ref, 1.5e-2, 2e-3, "cfg+ddim")
+    assert torch.equal(l1, trace)
+    l2 = lat.clone()
+    ops.cfg_ddim_composite(eps, l2, coef, frozen=frozen, mask=mask)
+    ref2 = frozen.float() * mask.float() + ref * (1 - mask.float())
+    _close(l2, ref2, 1.5e-2, 2e-3, "cfg+ddim+composite")
+    assert torch.equal(l2[:, :, mask.bool()], frozen[:, :, mask.bool()])

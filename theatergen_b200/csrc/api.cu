@@ -34,4 +34,112 @@ int tg_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* W
   return tg::conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, e, HM(out), ldc, ST(stream));
 }
 
+
+int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
+                 const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream) {
+  TG_CHECK(x1 && gamma && beta && out && (C2 == 0 || x2), "tg_groupnorm: null pointer");
+  return tg::groupnorm_nhwc(H(x1), C1, H(x2), C2, B, HW, H(gamma), H(beta), eps, silu, HM(out), workspace, ST(stream));
+}
+
+int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* beta, float eps, tg_half* out,
+                 int ldo, int M, int C, void* stream) {
+  TG_CHECK(x && gamma && beta && out, "tg_layernorm: null pointer");
+  return tg::layernorm_rows(H(x), ldx, H(gamma), H(beta), eps, HM(out), ldo, M, C, ST(stream));
+}
+
+int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
+                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, void* stream) {
+  TG_CHECK(Q && K && V && O && Nq > 0 && Nk > 0, "tg_attention: bad arguments");
+  return tg::attention_flash(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, Nq, Nk, d, scale, ST(stream));
+}
+
+int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg_half* Vt, const tg_half* Ki,
+                          const tg_half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
+                          const tg_half* add_mask, tg_half* O, int ldo, tg_half* probs, int probs_b0, int B,
+                          int heads, int Nq, int d, float scale, void* stream) {
+  TG_CHECK(Q && Kt && Vt && O && (n_ip == 0 || (Ki && Vi)), "tg_attention_cross_ip: null pointer");
+  return tg::attention_cross_ip(H(Q), ldq, H(Kt), H(Vt), H(Ki), H(Vi), ldkv, n_text, n_ip, ip_scale, H(add_mask),
+                                HM(O), ldo, HM(probs), probs_b0, B, heads, Nq, d, scale, ST(stream));
+}
+
+int tg_upsample2x(const tg_half* x, int B, int Hh, int W, int C, tg_half* y, void* stream) {
+  TG_CHECK(x && y, "tg_upsample2x: null pointer");
+  return tg::upsample2x_nhwc(H(x), B, Hh, W, C, HM(y), ST(stream));
+}
+int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, void* stream) {
+  TG_CHECK(x && a, "tg_im2col_s2: null pointer");
+  return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), ST(stream));
+}
+int tg_conv_in(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int Cout,
+               void* stream) {
+  TG_CHECK(x && w && bias && y, "tg_conv_in: null pointer");
+  return tg::conv_in_nchw_to_nhwc(H(x), H(w), H(bias), HM(y), B, Hh, W, Cout, ST(stream));
+}
+int tg_conv_out(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int C,
+                void* stream) {
+  TG_CHECK(x && w && bias && y, "tg_conv_out: null pointer");
+  return tg::conv_out_nhwc_to_nchw(H(x), H(w), H(bias), HM(y), B, Hh, W, C, ST(stream));
+}
+int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream) {
+  TG_CHECK(t_dev && out && dim % 2 == 0, "tg_timestep_embedding: bad arguments");
+  return tg::timestep_embedding(t_dev, HM(out), B, dim, ST(stream));
+}
+int tg_add_inplace(tg_half* y, const tg_half* x, long long n, void* stream) {
+  TG_CHECK(x && y && n >= 0, "tg_add_inplace: bad arguments");
+  return tg::add_inplace(HM(y), H(x), (size_t)n, ST(stream));
+}
+int tg_nchw_to_nhwc(const tg_half* x, tg_half* y, int B, int C, int HW, void* stream) {
+  TG_CHECK(x && y, "tg_nchw_to_nhwc: null pointer");
+  return tg::nchw_to_nhwc(H(x), HM(y), B, C, HW, ST(stream));
+}
+int tg_duplicate_latents(const tg_half* lat, tg_half* out, int n, void* stream) {
+  TG_CHECK(lat && out, "tg_duplicate_latents: null pointer");
+  return tg::duplicate_latents(H(lat), HM(out), n, ST(stream));
+}
+int tg_cfg_ddim_composite(const tg_half* eps, tg_half* latents, const float* coef_dev, const tg_half* frozen,
+                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, void* stream) {
+  TG_CHECK(eps && latents && coef_dev && ((frozen == nullptr) == (mask == nullptr)), "tg_cfg_ddim_composite: bad arguments");
+  return tg::cfg_ddim_composite(H(eps), HM(latents), coef_dev, H(frozen), H(mask), K, C, HW, HM(latents_copy), ST(stream));
+}
+
+int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const int* map_hw, int n_keys,
+                       int heads, int n_tok, const double* boxes, const int* box_obj, int n_box,
+                       const tg_guidance_item* items, int n_items, const tg_guidance_item* ref_items,
+                       const tg_half* const* ref_maps, int n_ref_items, float fg_top_p, float bg_top_p,
+                       float fg_weight, float bg_weight, float grad_scale, float ref_eps, float* loss_out,
+                       float* workspace, void* stream) {
+  TG_CHECK(maps && map_hw && loss_out && workspace, "tg_guidance_energy: null pointer");
+  TG_CHECK(n_keys <= tg::GUIDANCE_MAX_KEYS && n_box <= tg::GUIDANCE_MAX_BOXES && n_items <= tg::GUIDANCE_MAX_ITEMS &&
+               n_ref_items <= tg::GUIDANCE_MAX_REF_ITEMS,
+           "tg_guidance_energy: limits are %d keys, %d boxes, %d items, %d ref items", tg::GUIDANCE_MAX_KEYS,
+           tg::GUIDANCE_MAX_BOXES, tg::GUIDANCE_MAX_ITEMS, tg::GUIDANCE_MAX_REF_ITEMS);
+  tg::GuidanceParams P{};
+  for (int k = 0; k < n_keys; ++k) {
+    P.maps[k] = H(maps[k]);
+    P.dmaps[k] = dmaps ? HM(dmaps[k]) : nullptr;
+    P.map_hw[k] = map_hw[k];
+  }
+  for (int b = 0; b < n_box; ++b) {
+    for (int j = 0; j < 4; ++j) P.boxes[b][j] = boxes[b * 4 + j];
+    P.box_obj[b] = box_obj[b];
+  }
+  for (int i = 0; i < n_items; ++i) {
+    P.items[i].key = items[i].key; P.items[i].obj = items[i].obj; P.items[i].box = items[i].box;
+    P.items[i].ref = items[i].ref; P.items[i].tok = items[i].tok; P.items[i].weight = items[i].weight;
+    TG_CHECK(items[i].key < n_keys && items[i].tok < n_tok, "tg_guidance_energy: item %d out of range", i);
+  }
+  for (int i = 0; i < n_ref_items; ++i) {
+    P.ref_items[i].key = ref_items[i].key; P.ref_items[i].obj = ref_items[i].obj; P.ref_items[i].box = ref_items[i].box;
+    P.ref_items[i].ref = ref_items[i].ref; P.ref_items[i].tok = ref_items[i].tok; P.ref_items[i].weight = ref_items[i].weight;
+    TG_CHECK(ref_items[i].key < n_keys && ref_items[i].tok < n_tok && ref_items[i].box < n_box && ref_maps,
+             "tg_guidance_energy: ref item %d out of range", i);
+    P.ref_maps[i] = H(ref_maps[ref_items[i].ref]);
+    P.ref_items[i].ref = (unsigned char)i;
+  }
+  P.n_keys = n_keys; P.n_box = n_box; P.n_items = n_items; P.n_ref_items = n_ref_items; P.heads = heads; P.n_tok = n_tok;
+  P.fg_top_p = fg_top_p; P.bg_top_p = bg_top_p; P.fg_weight = fg_weight; P.bg_weight = bg_weight;
+  P.grad_scale = grad_scale; P.ref_eps = ref_eps;
+  return tg::guidance_energy(P, loss_out, workspace, ST(stream));
+}
+
 }  // extern "C"

@@ -1,0 +1,283 @@
+// Small HBM/latency-bound kernels around the tensor-core ones.
+#include "common.cuh"
+#include "ops.h"
+
+namespace tg {
+
+// ---------------------------------------------------------------------------------------------------------
+// nearest x2 upsample, NHWC (diffusers Upsample2D: F.interpolate(scale_factor=2, mode="nearest") before its conv;
+// call sites ip_adapter/unet_2d_blocks.py:2251,2332).  16-byte vectors, each input vector written 4 times.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    size_t p = i / C8;
+    const int ox = (int)(p % (2 * W));
+    p /= (2 * W);
+    const int oy = (int)(p % (2 * H));
+    const int b = (int)(p / (2 * H));
+    y[i] = x[(((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * C8 + c];
+  }
+}
+
+int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st) {
+  TG_CHECK(C % 8 == 0, "upsample: C %% 8 != 0");
+  const size_t total = (size_t)B * 4 * H * W * (C / 8);
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
+  upsample2x_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C / 8,
+                                          total);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// im2col for the three stride-2 3x3 convs (diffusers Downsample2D, pad 1; ip_adapter/unet_2d_blocks.py:1112,1198)
+// A[b*Ho*Wo + oy*Wo + ox][(ky*3+kx)*C + c] = x[b][2oy+ky-1][2ox+kx-1][c]  (0 outside)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int H, int W, int C8, size_t total) {
+  const int Ho = H / 2, Wo = W / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    size_t p = i / C8;
+    const int tap = (int)(p % 9);
+    p /= 9;
+    const int ox = (int)(p % Wo);
+    p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)b * H + iy) * W + ix) * C8 + c];
+    a[i] = v;
+  }
+}
+
+int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaStream_t st) {
+  TG_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad dims");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
+  im2col_s2_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(a), H, W, C / 8,
+                                         total);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv_in: NCHW [B,4,H,W] -> NHWC [B,H,W,320], 3x3 pad 1 (ip_adapter/unet_2d_condition.py:999)
+// weights kept in torch layout [Cout][Cin][3][3]; K = 36 -> CUDA cores, weights in shared memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int CIN, int PIX>
+__global__ void __launch_bounds__(256)
+conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+               __half* __restrict__ y, int H, int W, int Cout) {
+  extern __shared__ float sm_ci[];
+  float* sw = sm_ci;                        // [CIN*9][Cout]
+  float* sp = sw + CIN * 9 * Cout;          // [PIX][CIN*9]
+  const int b = blockIdx.y, p0 = blockIdx.x * PIX, HW = H * W;
+  for (int i = threadIdx.x; i < CIN * 9 * Cout; i += blockDim.x) {
+    const int co = i / (CIN * 9), k = i % (CIN * 9);
+    sw[k * Cout + co] = __half2float(w[i]);
+  }
+  for (int i = threadIdx.x; i < PIX * CIN * 9; i += blockDim.x) {
+    const int pp = i / (CIN * 9), k = i % (CIN * 9);
+    const int ci = k / 9, tap = k % 9;
+    const int p = p0 + pp, yy = p / W + tap / 3 - 1, xx = p % W + tap % 3 - 1;
+    float v = 0.f;
+    if (p < HW && yy >= 0 && yy < H && xx >= 0 && xx < W) v = __half2float(x[(((size_t)b * CIN + ci) * H + yy) * W + xx]);
+    sp[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PIX * Cout; i += blockDim.x) {
+    const int pp = i / Cout, co = i % Cout;
+    if (p0 + pp >= HW) continue;
+    float acc = __half2float(bias[co]);
+#pragma unroll
+    for (int k = 0; k < CIN * 9; ++k) acc += sp[pp * CIN * 9 + k] * sw[k * Cout + co];
+    y[((size_t)b * HW + p0 + pp) * Cout + co] = __float2half_rn(acc);
+  }
+}
+
+int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W,
+                         int Cout, cudaStream_t st) {
+  constexpr int CIN = 4, PIX = 32;
+  const size_t smem = (size_t)(CIN * 9 * Cout + PIX * CIN * 9) * sizeof(float);
+  auto kern = conv_in_kernel<CIN, PIX>;
+  static bool attr = false;
+  if (!attr) {
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  TG_CHECK(smem <= 96 * 1024, "conv_in: Cout=%d too large", Cout);
+  kern<<<dim3((H * W + PIX - 1) / PIX, B), 256, smem, st>>>(x, w, bias, y, H, W, Cout);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv_out: NHWC [B,H,W,C] (already GroupNorm+SiLU-ed) -> NCHW [B,4,H,W], 3x3 pad 1
+// (ip_adapter/unet_2d_condition.py:1120).  One warp per output pixel; weights [4][3][3][C] via L1.
+// ---------------------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                __half* __restrict__ y, int B, int H, int W, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int HW = H * W;
+  if (warp >= B * HW) return;
+  const int b = warp / HW, p = warp % HW, py = p / W, px = p % W;
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  const int c2n = C / 2;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xx) * C);
+    for (int c = lane; c < c2n; c += 32) {
+      const float2 xv = __half22float2(xp[c]);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float2 wv = __half22float2(__ldg(reinterpret_cast<const __half2*>(w + ((size_t)o * 9 + tap) * C) + c));
+        acc[o] += xv.x * wv.x + xv.y * wv.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    const float s = warp_sum(acc[o]);
+    if (lane == 0) y[((size_t)b * COUT + o) * HW + p] = __float2half_rn(s + __half2float(bias[o]));
+  }
+}
+
+int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
+                          cudaStream_t st) {
+  TG_CHECK(C % 2 == 0, "conv_out: C odd");
+  const int warps = B * H * W;
+  conv_out_kernel<4><<<(warps * 32 + 255) / 256, 256, 0, st>>>(x, w, bias, y, B, H, W, C);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Timesteps(320, flip_sin_to_cos=True, shift=0): out[b] = [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half)
+// computed in fp32 then cast to fp16 (ip_adapter/unet_2d_condition.py:897-902).  t is read from device memory so a
+// captured CUDA graph can be replayed for every timestep.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void timestep_embed_kernel(const float* __restrict__ t, __half* __restrict__ out, int dim) {
+  const int b = blockIdx.x, half_dim = dim / 2;
+  const float tv = t[b];
+  for (int i = threadIdx.x; i < half_dim; i += blockDim.x) {
+    const float f = expf(-9.210340371976184f * (float)i / (float)half_dim);
+    const float e = tv * f;
+    out[(size_t)b * dim + i] = __float2half_rn(cosf(e));
+    out[(size_t)b * dim + half_dim + i] = __float2half_rn(sinf(e));
+  }
+}
+
+int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st) {
+  timestep_embed_kernel<<<B, 160, 0, st>>>(t_dev, out, dim);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// y += x (ControlNet residual adds, ip_adapter/unet_2d_condition.py:1044-1053, 1077-1078)
+__global__ void __launch_bounds__(256) add_inplace_kernel(__half2* __restrict__ y, const __half2* __restrict__ x, size_t n2) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __hadd2(y[i], x[i]);
+}
+int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st) {
+  TG_CHECK(n % 2 == 0, "add: odd length");
+  const int grid = (int)(((n / 2 + 255) / 256) < (size_t)(148 * 8) ? ((n / 2 + 255) / 256) : (size_t)(148 * 8));
+  add_inplace_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<__half2*>(y), reinterpret_cast<const __half2*>(x), n / 2);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// NCHW <-> NHWC for the (tiny) ControlNet residual interface
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int HW, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const int hw = (int)(p % HW);
+    const size_t b = p / HW;
+    y[i] = x[(b * C + c) * HW + hw];
+  }
+}
+int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t st) {
+  const size_t total = (size_t)B * C * HW;
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
+  nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, C, HW, total);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused classifier-free guidance + DDIM step + masked composite, one launch per denoise step
+//   eps    = eps_u + g (eps_c - eps_u)                                  (models/pipelines.py:441-442, 820-821)
+//   x0     = (x - sqrt(1-a_t) eps) / sqrt(a_t);  x' = sqrt(a_prev) x0 + sqrt(1-a_prev) eps     (DDIM, eta = 0)
+//   x'     = frozen * m + x' * (1 - m)     when frozen != null          (models/pipelines.py:833-834)
+// eps is [2K,4,H,W] (first K rows unconditional), latents [K,4,H,W]; coef = {g, sqrt(a_t), sqrt(1-a_t),
+// sqrt(a_prev), sqrt(1-a_prev)} lives in device memory (graph replay).  mask is [H,W] broadcast over K and C.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cfg_ddim_kernel(const __half* __restrict__ eps, __half* __restrict__ lat, const float* __restrict__ coef,
+                const __half* __restrict__ frozen, const __half* __restrict__ mask, int K, int CHW, int HW,
+                __half* __restrict__ lat_copy) {
+  const float g = coef[0], sa = coef[1], s1a = coef[2], sap = coef[3], s1ap = coef[4];
+  const int total = K * CHW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i / CHW, r = i % CHW;
+    const float eu = __half2float(eps[(size_t)k * CHW + r]);
+    const float ec = __half2float(eps[(size_t)(K + k) * CHW + r]);
+    // every intermediate of the reference is an fp16 tensor (fp32 python/0-d scalars do not promote)
+    const float e = __half2float(__float2half_rn(eu + g * (ec - eu)));
+    const float x = __half2float(lat[i]);
+    const float x0 = (x - s1a * e) / sa;
+    float xn = sap * x0 + s1ap * e;
+    if (frozen != nullptr) {
+      const float m = __half2float(mask[r % HW]);
+      xn = __half2float(frozen[i]) * m + __half2float(__float2half_rn(xn)) * (1.f - m);
+    }
+    const __half o = __float2half_rn(xn);
+    lat[i] = o;
+    if (lat_copy != nullptr) lat_copy[i] = o;
+  }
+}
+
+int cfg_ddim_composite(const __half* eps, __half* latents, const float* coef_dev, const __half* frozen,
+                       const __half* mask, int K, int C, int HW, __half* latents_copy, cudaStream_t st) {
+  const int total = K * C * HW;
+  cfg_ddim_kernel<<<(total + 255) / 256, 256, 0, st>>>(eps, latents, coef_dev, frozen, mask, K, C * HW, HW,
+                                                       latents_copy);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// duplicate latents for CFG: x_in[2K] = cat([latents]*2) (models/pipelines.py:409, 747)
+__global__ void __launch_bounds__(256)
+dup_kernel(const __half* __restrict__ lat, __half* __restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const __half v = lat[i];
+    out[i] = v;
+    out[n + i] = v;
+  }
+}
+int duplicate_latents(const __half* lat, __half* out, int n, cudaStream_t st) {
+  dup_kernel<<<(n + 255) / 256, 256, 0, st>>>(lat, out, n);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tg

@@ -23,4 +23,57 @@ int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, 
 int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, const EpilogueSpec& e,
                  __half* out, int ldc, cudaStream_t st);
 
+
+// GroupNorm(32 groups)(+SiLU) over the channel-concat [x1 | x2] (x2 may be null, C2 = 0); fp32 statistics.
+// workspace: >= B*64*32*2 floats.
+int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
+                   const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st);
+int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* beta, float eps, __half* out,
+                   int ldo, int M, int C, cudaStream_t st);
+
+// O[b, n, h*d..] = softmax(scale * Q K^T) V per (b, h); row pitches in elements
+int attention_flash(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
+                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t st);
+// text + image-token cross attention (see attn.cu)
+int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
+                       const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
+                       const __half* add_mask, __half* O, int ldo, __half* probs, int probs_b0, int B, int heads,
+                       int Nq, int d, float scale, cudaStream_t st);
+
+
+int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
+int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaStream_t st);
+int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W,
+                         int Cout, cudaStream_t st);
+int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
+                          cudaStream_t st);
+int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st);
+int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st);
+int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t st);
+int cfg_ddim_composite(const __half* eps, __half* latents, const float* coef_dev, const __half* frozen,
+                       const __half* mask, int K, int C, int HW, __half* latents_copy, cudaStream_t st);
+int duplicate_latents(const __half* lat, __half* out, int n, cudaStream_t st);
+
+// ---- guidance energy (guidance.cu); the whole description travels as a kernel parameter (graph capturable) ----
+static constexpr int GUIDANCE_MAX_KEYS = 8, GUIDANCE_MAX_BOXES = 16, GUIDANCE_MAX_ITEMS = 128,
+                     GUIDANCE_MAX_REF_ITEMS = 32, GUIDANCE_MAX_HW = 256;
+struct GuidanceItem {
+  unsigned char key, obj, box, ref;
+  int tok;
+  float weight;
+};
+struct GuidanceParams {
+  const __half* maps[GUIDANCE_MAX_KEYS];      // [heads, HW, n_tok] each
+  __half* dmaps[GUIDANCE_MAX_KEYS];           // nullable, same shape: d(energy*grad_scale)/d(map), accumulated
+  const __half* ref_maps[GUIDANCE_MAX_REF_ITEMS];  // [heads, HW] each
+  int map_hw[GUIDANCE_MAX_KEYS];
+  double boxes[GUIDANCE_MAX_BOXES][4];        // normalised x0,y0,x1,y1 (python floats)
+  int box_obj[GUIDANCE_MAX_BOXES];
+  GuidanceItem items[GUIDANCE_MAX_ITEMS];
+  GuidanceItem ref_items[GUIDANCE_MAX_REF_ITEMS];
+  int n_keys, n_box, n_items, n_ref_items, heads, n_tok;
+  float fg_top_p, bg_top_p, fg_weight, bg_weight, grad_scale, ref_eps;
+};
+int guidance_energy(const GuidanceParams& P, float* loss_out, float* workspace, cudaStream_t st);
+
 }  // namespace tg

@@ -61,3 +61,156 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, out_scale=1.0, out=
                                0 if res2 is None else res2.stride(0), float(out_scale), _p(out), Cout, _stream())
     _lib.check(rc, "tg_conv3x3")
     return out
+
+
+_GN_WS = {}
+
+
+def _gn_workspace(device, B):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _GN_WS.get(key)
+    if ws is None or ws.numel() < B * 64 * 32 * 2:
+        ws = torch.empty(max(B, 16) * 64 * 32 * 2, dtype=torch.float32, device=device)
+        _GN_WS[key] = ws
+    return ws
+
+
+def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=False, out=None, workspace=None):
+    """GroupNorm(32)(+SiLU) over channels-last [B,HW,C1] (| x2 [B,HW,C2]) -> [B,HW,C1+C2]."""
+    _chk16(x1, x2, gamma, beta, out)
+    B, HW, C1 = x1.shape
+    C2 = 0 if x2 is None else x2.shape[-1]
+    assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
+    if out is None:
+        out = torch.empty((B, HW, C1 + C2), dtype=torch.float16, device=x1.device)
+    ws = workspace if workspace is not None else _gn_workspace(x1.device, B)
+    rc = _lib.lib().tg_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, _p(gamma), _p(beta), float(eps), int(silu), _p(out),
+                                 _p(ws), _stream())
+    _lib.check(rc, "tg_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _chk16(x, gamma, beta, out)
+    M, Cc = x.shape
+    if out is None:
+        out = torch.empty((M, Cc), dtype=torch.float16, device=x.device)
+    rc = _lib.lib().tg_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), _p(out), out.stride(0), M, Cc,
+                                 _stream())
+    _lib.check(rc, "tg_layernorm")
+    return out
+
+
+def attention(q, k, v, B, heads, scale=None, out=None):
+    """q [B*Nq, heads*d] (row pitch may exceed), k/v [B*Nk, heads*d] views -> out [B*Nq, heads*d]."""
+    _chk16(q, k, v, out)
+    d = q.shape[1] // heads
+    Nq, Nk = q.shape[0] // B, k.shape[0] // B
+    if scale is None:
+        scale = d ** -0.5
+    if out is None:
+        out = torch.empty((B * Nq, heads * d), dtype=torch.float16, device=q.device)
+    rc = _lib.lib().tg_attention(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out), out.stride(0), B,
+                                 heads, Nq, Nk, d, float(scale), _stream())
+    _lib.check(rc, "tg_attention")
+    return out
+
+
+def attention_cross_ip(q, kt, vt, ki, vi, B, heads, n_text, n_ip, ip_scale=None, add_mask=None, probs=None,
+                       probs_b0=0, out=None):
+    """q [B*Nq, C]; kt/vt/ki/vi column views [B*(n_text+n_ip), C] of the K/V projection buffer."""
+    _chk16(q, kt, vt, ki, vi, add_mask, probs, out)
+    Cc = q.shape[1]
+    d = Cc // heads
+    Nq = q.shape[0] // B
+    assert kt.stride(0) == vt.stride(0) and (ki is None or ki.stride(0) == kt.stride(0) == vi.stride(0))
+    if ip_scale is not None:
+        assert ip_scale.dtype == torch.float32 and ip_scale.numel() == B and ip_scale.is_cuda
+    if out is None:
+        out = torch.empty((B * Nq, Cc), dtype=torch.float16, device=q.device)
+    rc = _lib.lib().tg_attention_cross_ip(_p(q), q.stride(0), _p(kt), _p(vt), _p(ki), _p(vi), kt.stride(0), n_text, n_ip,
+                                          _p(ip_scale), _p(add_mask), _p(out), out.stride(0), _p(probs), probs_b0, B,
+                                          heads, Nq, d, float(d ** -0.5), _stream())
+    _lib.check(rc, "tg_attention_cross_ip")
+    return out
+
+
+def upsample2x(x, out=None):
+    _chk16(x, out)
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_upsample2x(_p(x), B, H, W, Cc, _p(out), _stream()), "tg_upsample2x")
+    return out
+
+
+def im2col_s2(x, out=None):
+    _chk16(x, out)
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B * (H // 2) * (W // 2), 9 * Cc), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_im2col_s2(_p(x), B, H, W, Cc, _p(out), _stream()), "tg_im2col_s2")
+    return out
+
+
+def conv_in(x_nchw, w, bias, out=None):
+    _chk16(x_nchw, w, bias, out)
+    B, Cin, H, W = x_nchw.shape
+    assert Cin == 4 and x_nchw.is_contiguous() and w.is_contiguous()
+    Cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x_nchw.device)
+    _lib.check(_lib.lib().tg_conv_in(_p(x_nchw), _p(w), _p(bias), _p(out), B, H, W, Cout, _stream()), "tg_conv_in")
+    return out
+
+
+def conv_out(x_nhwc, w, bias, out=None):
+    """w packed [4,3,3,C]; returns NCHW [B,4,H,W]."""
+    _chk16(x_nhwc, w, bias, out)
+    B, H, W, Cc = x_nhwc.shape
+    if out is None:
+        out = torch.empty((B, 4, H, W), dtype=torch.float16, device=x_nhwc.device)
+    _lib.check(_lib.lib().tg_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(out), B, H, W, Cc, _stream()), "tg_conv_out")
+    return out
+
+
+def timestep_embedding(t_dev, dim=320, out=None):
+    assert t_dev.dtype == torch.float32 and t_dev.is_cuda
+    B = t_dev.numel()
+    if out is None:
+        out = torch.empty((B, dim), dtype=torch.float16, device=t_dev.device)
+    _lib.check(_lib.lib().tg_timestep_embedding(_p(t_dev), _p(out), B, dim, _stream()), "tg_timestep_embedding")
+    return out
+
+
+def add_inplace(y, x):
+    _chk16(y, x)
+    assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+    _lib.check(_lib.lib().tg_add_inplace(_p(y), _p(x), y.numel(), _stream()), "tg_add_inplace")
+    return y
+
+
+def nchw_to_nhwc(x, out=None):
+    _chk16(x, out)
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_nchw_to_nhwc(_p(x), _p(out), B, Cc, H * W, _stream()), "tg_nchw_to_nhwc")
+    return out
+
+
+def duplicate_latents(lat, out):
+    _chk16(lat, out)
+    _lib.check(_lib.lib().tg_duplicate_latents(_p(lat), _p(out), lat.numel(), _stream()), "tg_duplicate_latents")
+    return out
+
+
+def cfg_ddim_composite(eps, latents, coef_dev, frozen=None, mask=None, latents_copy=None):
+    """eps [2K,C,H,W], latents [K,C,H,W] updated in place; coef_dev float32[5] on device."""
+    _chk16(eps, latents, frozen, mask, latents_copy)
+    K, Cc, H, W = latents.shape
+    assert eps.shape[0] == 2 * K and coef_dev.dtype == torch.float32 and coef_dev.numel() >= 5
+    rc = _lib.lib().tg_cfg_ddim_composite(_p(eps), _p(latents), _p(coef_dev), _p(frozen), _p(mask), K, Cc, H * W,
+                                          _p(latents_copy), _stream())
+    _lib.check(rc, "tg_cfg_ddim_composite")
+    return latents

@@ -1,0 +1,319 @@
+"""TGUNet -- the SD-1.5 UNet forward executed entirely by libtheatergen.so kernels (module-level drop-in for
+`adapter.pipe.unet`, called exactly like the reference calls the diffusers module:
+models/pipelines.py:428 (stage 1), :802-816 (stage 2, with ControlNet residuals), :90 (guidance, with
+save_attn_to_dict / save_keys in cross_attention_kwargs)).
+
+Data layout in HBM: activations are channels-last fp16 -- images [B,H,W,C], tokens [B*H*W, C] (the same bytes,
+so the reference's NCHW<->NHWC permutes around every Transformer2DModel disappear); weights are repacked once:
+  conv3x3 [Cout,3,3,Cin]; q/k/v of self-attention fused [3C,C]; to_k/to_v/to_k_ip/to_v_ip of all 16
+  cross-attentions fused into one [sum 4C, 768] matrix (one GEMM per forward projects the context for every
+  layer); the 22 time_emb_proj fused into one [20160,1280] matrix; GEGLU rows interleaved per 64.
+The wiring follows ip_adapter/unet_2d_condition.py:799-1125 and the block files cited in oracle/unet.py.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .weights import pack_conv3x3, pack_geglu
+
+BLOCK_OUT = (320, 640, 1280, 1280)
+HEADS = 8
+
+
+class UNetOutput:
+    """Stand-in for diffusers' UNet2DConditionOutput: `.sample`, and `[0]` for return_dict=False call sites."""
+
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class _Config(dict):
+    __getattr__ = dict.__getitem__
+
+
+class IPAttnProcessorHandle:
+    """What `unet.attn_processors` holds for attn2 layers: carries the reference's mutable `scale` attribute
+    (ip_adapter/attention_processor.py:415; mutated by IPAdapter.set_scale, ip_adapter/ip_adapter.py:155-158)."""
+
+    def __init__(self, hidden_size, cross_attention_dim, scale=1.0, num_tokens=4):
+        self.hidden_size, self.cross_attention_dim = hidden_size, cross_attention_dim
+        self.scale, self.num_tokens = scale, num_tokens
+
+
+class AttnProcessorHandle:
+    pass
+
+
+def _resnet_specs():
+    out, ch, skips = [], BLOCK_OUT[0], [BLOCK_OUT[0]]
+    for i, co in enumerate(BLOCK_OUT):
+        for j in range(2):
+            out.append((f"down_blocks.{i}.resnets.{j}", ch, 0, co))
+            ch = co
+            skips.append(ch)
+        if i < 3:
+            skips.append(ch)
+    out += [("mid_block.resnets.0", ch, 0, ch), ("mid_block.resnets.1", ch, 0, ch)]
+    for i, co in enumerate(reversed(BLOCK_OUT)):
+        for j in range(3):
+            s = skips.pop()
+            out.append((f"up_blocks.{i}.resnets.{j}", ch, s, co))
+            ch = co
+    return out
+
+
+def _transformer_specs():
+    out = []
+    for i in range(3):
+        for j in range(2):
+            out.append((f"down_blocks.{i}.attentions.{j}", BLOCK_OUT[i], ("down", i, j, 0)))
+    rev = list(reversed(BLOCK_OUT))
+    for i in range(1, 4):
+        for j in range(3):
+            out.append((f"up_blocks.{i}.attentions.{j}", rev[i], ("up", i, j, 0)))
+    out.append(("mid_block.attentions.0", 1280, ("mid", 0, 0, 0)))
+    return out
+
+
+class TGUNet:
+    dtype = torch.float16
+
+    def __init__(self, state_dict, device="cuda", num_ip_tokens=4, cross_attention_dim=768):
+        self.device = torch.device(device)
+        self.num_ip_tokens = num_ip_tokens
+        self.config = _Config(in_channels=4, cross_attention_dim=cross_attention_dim, block_out_channels=BLOCK_OUT,
+                              sample_size=64)
+        self._pack(state_dict)
+        self.attn_processors = {}
+        for p, c, _ in _transformer_specs():
+            self.attn_processors[f"{p}.transformer_blocks.0.attn1.processor"] = AttnProcessorHandle()
+            self.attn_processors[f"{p}.transformer_blocks.0.attn2.processor"] = IPAttnProcessorHandle(
+                c, cross_attention_dim, 1.0, num_ip_tokens)
+        self.ip_scale_per_sample = None  # optional float32 [B] device tensor (co-batched characters)
+        self._scale_buf = {}
+
+    # -------------------------------------------------------------------------------------------------
+    def _pack(self, sd):
+        dev = self.device
+
+        def g(name):
+            return sd[name].to(device=dev, dtype=torch.float16).contiguous()
+
+        w = {}
+        w["conv_in.w"], w["conv_in.b"] = g("conv_in.weight"), g("conv_in.bias")
+        w["t1.w"], w["t1.b"] = g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias")
+        w["t2.w"], w["t2.b"] = g("time_embedding.linear_2.weight"), g("time_embedding.linear_2.bias")
+        self.resnets = {}
+        tw, tb, off = [], [], 0
+        for p, c1, c2, co in _resnet_specs():
+            cin = c1 + c2
+            r = dict(cin=cin, cout=co, temb_off=off)
+            r["n1g"], r["n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
+            r["c1w"], r["c1b"] = pack_conv3x3(g(p + ".conv1.weight")), g(p + ".conv1.bias")
+            r["n2g"], r["n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
+            r["c2w"], r["c2b"] = pack_conv3x3(g(p + ".conv2.weight")), g(p + ".conv2.bias")
+            if (p + ".conv_shortcut.weight") in sd:
+                r["scw"] = g(p + ".conv_shortcut.weight").reshape(co, cin).contiguous()
+                r["scb"] = g(p + ".conv_shortcut.bias")
+            tw.append(g(p + ".time_emb_proj.weight"))
+            tb.append(g(p + ".time_emb_proj.bias"))
+            off += co
+            self.resnets[p] = r
+        w["temb.w"], w["temb.b"] = torch.cat(tw, 0).contiguous(), torch.cat(tb, 0).contiguous()
+        self.transformers = {}
+        kvw, off = [], 0
+        has_ip = any(k.endswith("processor.to_k_ip.weight") for k in sd)
+        self.has_ip = has_ip
+        for p, c, key in _transformer_specs():
+            tb_ = p + ".transformer_blocks.0"
+            t = dict(C=c, key=key, kv_off=off)
+            t["ng"], t["nb"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+            t["piw"], t["pib"] = g(p + ".proj_in.weight").reshape(c, c).contiguous(), g(p + ".proj_in.bias")
+            t["pow"], t["pob"] = g(p + ".proj_out.weight").reshape(c, c).contiguous(), g(p + ".proj_out.bias")
+            for n in ("norm1", "norm2", "norm3"):
+                t[n + "g"], t[n + "b"] = g(f"{tb_}.{n}.weight"), g(f"{tb_}.{n}.bias")
+            t["qkvw"] = torch.cat([g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"], 0).contiguous()
+            t["o1w"], t["o1b"] = g(f"{tb_}.attn1.to_out.0.weight"), g(f"{tb_}.attn1.to_out.0.bias")
+            t["q2w"] = g(f"{tb_}.attn2.to_q.weight")
+            t["o2w"], t["o2b"] = g(f"{tb_}.attn2.to_out.0.weight"), g(f"{tb_}.attn2.to_out.0.bias")
+            rows = [g(f"{tb_}.attn2.to_k.weight"), g(f"{tb_}.attn2.to_v.weight")]
+            if has_ip:
+                rows += [g(f"{tb_}.attn2.processor.to_k_ip.weight"), g(f"{tb_}.attn2.processor.to_v_ip.weight")]
+            kvw += rows
+            off += c * len(rows)
+            t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
+            t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
+            self.transformers[p] = t
+        w["ctxkv.w"] = torch.cat(kvw, 0).contiguous()
+        for i in range(3):
+            c = BLOCK_OUT[i]
+            w[f"down{i}.w"] = pack_conv3x3(g(f"down_blocks.{i}.downsamplers.0.conv.weight")).reshape(c, 9 * c)
+            w[f"down{i}.b"] = g(f"down_blocks.{i}.downsamplers.0.conv.bias")
+        rev = list(reversed(BLOCK_OUT))
+        for i in range(3):
+            w[f"up{i}.w"] = pack_conv3x3(g(f"up_blocks.{i}.upsamplers.0.conv.weight"))
+            w[f"up{i}.b"] = g(f"up_blocks.{i}.upsamplers.0.conv.bias")
+        w["no.g"], w["no.b"] = g("conv_norm_out.weight"), g("conv_norm_out.bias")
+        w["conv_out.w"], w["conv_out.b"] = pack_conv3x3(g("conv_out.weight")), g("conv_out.bias")
+        self.w = w
+
+    def weight_bytes(self):
+        n = sum(v.numel() for v in self.w.values())
+        for d in list(self.resnets.values()) + list(self.transformers.values()):
+            n += sum(v.numel() for v in d.values() if torch.is_tensor(v))
+        return 2 * n
+
+    # -------------------------------------------------------------------------------------------------
+    def _resnet(self, p, x1, x2, temb_all, B, H, W):
+        r = self.resnets[p]
+        cin, co = r["cin"], r["cout"]
+        HW = H * W
+        n1 = ops.groupnorm(x1.view(B, HW, -1), r["n1g"], r["n1b"], 1e-5, x2=None if x2 is None else x2.view(B, HW, -1),
+                           silu=True)
+        h = ops.conv3x3(n1.view(B, H, W, cin), r["c1w"], r["c1b"],
+                        rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co])
+        n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True)
+        if "scw" in r:
+            sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
+            sc = sc.view(B, H, W, co)
+        else:
+            assert x2 is None
+            sc = x1
+        return ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc)
+
+    def _transformer(self, p, x, ctxkv, B, H, W, n_text, n_ip, ip_scale, capture, save_keys, cond_only, token_idx):
+        t = self.transformers[p]
+        C, M = t["C"], B * H * W
+        n = ops.groupnorm(x.view(B, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
+        h = ops.gemm(n.view(M, C), t["piw"], t["pib"])
+        # self attention
+        ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
+        qkv = ops.gemm(ln, t["qkvw"])
+        a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
+        h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
+        # cross attention (+ image tokens)
+        ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
+        q = ops.gemm(ln, t["q2w"])
+        o = t["kv_off"]
+        probs, b0 = None, 0
+        if capture is not None and (save_keys is None or t["key"] in save_keys):
+            b0 = B // 2 if cond_only else 0
+            probs = torch.empty((B - b0, HEADS, H * W, n_text), dtype=torch.float16, device=x.device)
+        a = ops.attention_cross_ip(q, ctxkv[:, o:o + C], ctxkv[:, o + C:o + 2 * C],
+                                   ctxkv[:, o + 2 * C:o + 3 * C] if n_ip else None,
+                                   ctxkv[:, o + 3 * C:o + 4 * C] if n_ip else None, B, HEADS, n_text, n_ip,
+                                   ip_scale=ip_scale if n_ip else None, probs=probs, probs_b0=b0)
+        if probs is not None:
+            if token_idx is not None:
+                probs = probs[..., token_idx:token_idx + 1] if isinstance(token_idx, int) else probs[..., token_idx]
+            capture[t["key"]] = probs
+        h = ops.gemm(a, t["o2w"], t["o2b"], residual=h)
+        # feed forward (GEGLU fused in the GEMM epilogue)
+        ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
+        ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
+        h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
+        return ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C)).view(B, H, W, C)
+
+    def _ip_scale_tensor(self, B):
+        if self.ip_scale_per_sample is not None:
+            assert self.ip_scale_per_sample.numel() == B
+            return self.ip_scale_per_sample
+        s = float(next(p.scale for p in self.attn_processors.values() if isinstance(p, IPAttnProcessorHandle)))
+        key = (B, s)
+        if key not in self._scale_buf:
+            self._scale_buf[key] = torch.full((B,), s, dtype=torch.float32, device=self.device)
+        return self._scale_buf[key]
+
+    # -------------------------------------------------------------------------------------------------
+    def forward_raw(self, sample, t_dev, ctx, ip_scale=None, down_residuals=None, mid_residual=None, capture=None,
+                    save_keys=None, cond_only=False, token_idx=None):
+        """sample [B,4,H,W] fp16 (B even), t_dev float32 [B] on device, ctx [B,T,768] fp16 -> eps [B,4,H,W]."""
+        w = self.w
+        B, _, H, W = sample.shape
+        assert B % 2 == 0, "co-batched CFG pairs: batch must be even"
+        T = ctx.shape[1]
+        n_ip = self.num_ip_tokens if self.has_ip else 0
+        n_text = T - n_ip
+        if n_ip and ip_scale is None:
+            ip_scale = self._ip_scale_tensor(B)
+        emb = ops.timestep_embedding(t_dev, 320)
+        emb = ops.gemm(emb, w["t1.w"], w["t1.b"], act=ops.TG_ACT_SILU)
+        emb = ops.gemm(emb, w["t2.w"], w["t2.b"], act=ops.TG_ACT_SILU)  # = silu(time_embedding(t)), its only use
+        temb_all = ops.gemm(emb, w["temb.w"], w["temb.b"])
+        ctxkv = ops.gemm(ctx.reshape(B * T, -1), w["ctxkv.w"])
+
+        def tf(p, x, h_, w_):
+            return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
+                                     token_idx)
+
+        x = ops.conv_in(sample, w["conv_in.w"], w["conv_in.b"])
+        skips = [x]
+        h_, w_ = H, W
+        for i in range(4):
+            for j in range(2):
+                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all, B, h_, w_)
+                if i < 3:
+                    x = tf(f"down_blocks.{i}.attentions.{j}", x, h_, w_)
+                skips.append(x)
+            if i < 3:
+                c = BLOCK_OUT[i]
+                x = ops.gemm(ops.im2col_s2(x), w[f"down{i}.w"], w[f"down{i}.b"]).view(B, h_ // 2, w_ // 2, c)
+                h_, w_ = h_ // 2, w_ // 2
+                skips.append(x)
+        if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
+            skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
+        x = self._resnet("mid_block.resnets.0", x, None, temb_all, B, h_, w_)
+        x = tf("mid_block.attentions.0", x, h_, w_)
+        x = self._resnet("mid_block.resnets.1", x, None, temb_all, B, h_, w_)
+        if mid_residual is not None:
+            x = ops.add_inplace(x, ops.nchw_to_nhwc(mid_residual))
+        for i in range(4):
+            for j in range(3):
+                x = self._resnet(f"up_blocks.{i}.resnets.{j}", x, skips.pop(), temb_all, B, h_, w_)
+                if i > 0:
+                    x = tf(f"up_blocks.{i}.attentions.{j}", x, h_, w_)
+            if i < 3:
+                x = ops.conv3x3(ops.upsample2x(x), w[f"up{i}.w"], w[f"up{i}.b"])
+                h_, w_ = 2 * h_, 2 * w_
+        n = ops.groupnorm(x.view(B, h_ * w_, 320), w["no.g"], w["no.b"], 1e-5, silu=True)
+        return ops.conv_out(n.view(B, h_, w_, 320), w["conv_out.w"], w["conv_out.b"])
+
+    # the reference call surface (ip_adapter/unet_2d_condition.py:799-813)
+    def __call__(self, sample, timestep, encoder_hidden_states=None, cross_attention_kwargs=None,
+                 down_block_additional_residuals=None, mid_block_additional_residual=None, return_dict=True,
+                 **unused):
+        if not (sample.is_cuda and encoder_hidden_states.is_cuda):
+            raise RuntimeError("TGUNet runs on a CUDA device only (no CPU fallback)")
+        sample = sample.to(torch.float16).contiguous()
+        ctx = encoder_hidden_states.to(torch.float16).contiguous()
+        B = sample.shape[0]
+        pad = B % 2
+        if pad:  # guidance path runs the conditional half alone (models/pipelines.py:90)
+            sample, ctx = torch.cat([sample, sample[-1:]]), torch.cat([ctx, ctx[-1:]])
+        if torch.is_tensor(timestep) and timestep.is_cuda and timestep.dtype == torch.float32 and timestep.numel() == B + pad:
+            t_dev = timestep
+        else:
+            t_dev = torch.full((B + pad,), float(timestep), dtype=torch.float32, device=sample.device)
+        kw = cross_attention_kwargs or {}
+        capture = kw.get("save_attn_to_dict")
+        save_keys = kw.get("save_keys")
+        if save_keys is not None:
+            save_keys = [tuple(k) for k in save_keys]
+        cap_local = {} if capture is not None else None
+        eps = self.forward_raw(sample, t_dev, ctx, down_residuals=down_block_additional_residuals,
+                               mid_residual=mid_block_additional_residual, capture=cap_local, save_keys=save_keys,
+                               cond_only=bool(kw.get("return_cond_ca_only", False)) and not pad,
+                               token_idx=kw.get("return_token_ca_only"))
+        if capture is not None:
+            for k, v in cap_local.items():
+                v = v[:B] if pad else v
+                capture[k] = v.cpu() if kw.get("offload_cross_attn_to_cpu", False) else v
+        if pad:
+            eps = eps[:B]
+        return UNetOutput(eps) if return_dict else (eps,)
+
+    forward = __call__
