@@ -1,0 +1,85 @@
+"""Whole-path parity on the GPU: TGUNet (libtheatergen.so kernels) vs the oracle restatement of the reference UNet.
+
+Tolerance statement (north_star: "within a stated fp16 tolerance"): the reference computes in fp16 (fp16 softmax,
+fp16 storage of every intermediate).  We compare our fp16-storage / fp32-accumulate path against the oracle run in
+fp32, and measure the oracle's own fp16-vs-fp32 gap on the same inputs (= the reference's numeric noise floor on
+this GPU).  The test requires  max|ours - fp32| <= max(1.5 x max|fp16 oracle - fp32|, 4e-3)  and a relative
+RMS error below 2e-3.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+
+
+def _setup(B=2, seed=0):
+    from oracle import unet as OU
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = OU.synth_state_dict(1234)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 4, 64, 64, generator=g).half()
+    ctx = torch.randn(B, 81, 768, generator=g).half()
+    return OU, sd, x, ctx
+
+
+def _report(name, got, ref32, ref16=None):
+    e = (got.float() - ref32).abs()
+    out = {"max_abs": e.max().item(), "rel_rms": (e.pow(2).mean().sqrt() / ref32.pow(2).mean().sqrt()).item()}
+    if ref16 is not None:
+        e16 = (ref16.float() - ref32).abs()
+        out["fp16_oracle_max_abs"] = e16.max().item()
+        out["fp16_oracle_rel_rms"] = (e16.pow(2).mean().sqrt() / ref32.pow(2).mean().sqrt()).item()
+    print(name, out)
+    return out
+
+
+@pytest.mark.parametrize("B,t,scale", [(2, 981, 0.4), (4, 501, 0.0), (2, 1, 0.1)])
+def test_unet_forward_parity(B, t, scale):
+    from theatergen_b200.unet import TGUNet
+    OU, sd, x, ctx = _setup(B)
+    net = TGUNet(sd)
+    for p in net.attn_processors.values():
+        if hasattr(p, "scale"):
+            p.scale = scale
+    cap = {}
+    eps = net(x.cuda(), t, encoder_hidden_states=ctx.cuda(),
+              cross_attention_kwargs={"save_attn_to_dict": cap, "save_keys": KEYS}).sample
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    sd16 = {k: v.half().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        cap32 = {}
+        ref32 = OU.unet_forward(sd32, x.float().cuda(), t, ctx.float().cuda(), ip_scale=scale, capture=cap32,
+                                save_keys=KEYS)
+        ref16 = OU.unet_forward(sd16, x.cuda(), t, ctx.cuda(), ip_scale=scale)
+    r = _report(f"unet B={B} t={t}", eps, ref32, ref16)
+    assert r["max_abs"] <= max(1.5 * r["fp16_oracle_max_abs"], 4e-3), r
+    assert r["rel_rms"] <= 2e-3, r
+    for k in KEYS:
+        assert cap[k].shape == cap32[k].shape
+        assert (cap[k].float() - cap32[k]).abs().max().item() < 2e-3, k
+
+
+def test_unet_controlnet_residuals_and_odd_batch():
+    from theatergen_b200.unet import TGUNet
+    OU, sd, x, ctx = _setup(2)
+    net = TGUNet(sd)
+    g = torch.Generator().manual_seed(5)
+    shapes = [(320, 64)] * 3 + [(320, 32)] + [(640, 32)] * 2 + [(640, 16)] + [(1280, 16)] * 2 + [(1280, 8)] * 3
+    down = [(0.1 * torch.randn(2, c, s, s, generator=g)).half().cuda() for c, s in shapes]
+    mid = (0.1 * torch.randn(2, 1280, 8, 8, generator=g)).half().cuda()
+    eps = net(x.cuda(), 481, encoder_hidden_states=ctx.cuda(), down_block_additional_residuals=down,
+              mid_block_additional_residual=mid, return_dict=False)[0]
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = OU.unet_forward(sd32, x.float().cuda(), 481, ctx.float().cuda(), ip_scale=1.0,
+                              down_residuals=[d.float() for d in down], mid_residual=mid.float())
+    r = _report("unet+controlnet", eps, ref)
+    assert r["max_abs"] < 1.5e-2 and r["rel_rms"] < 2e-3, r
+    # conditional half alone (the guidance call, models/pipelines.py:90): B = 1 is padded internally
+    e1 = net(x[1:].cuda(), 481, encoder_hidden_states=ctx[1:].cuda()).sample
+    e2 = net(x.cuda(), 481, encoder_hidden_states=ctx.cuda()).sample
+    assert e1.shape == (1, 4, 64, 64)
+    assert torch.equal(e1, e2[1:])  # every kernel is deterministic and batch-position independent

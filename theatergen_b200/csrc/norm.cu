@@ -15,6 +15,7 @@ namespace tg {
 
 static constexpr int GN_GROUPS = 32;
 static constexpr int GN_MAX_SLABS = 64;
+static constexpr int GN_MAX_C = 2560;
 
 // partial[b][slab][g][2] = (sum, sumsq) over the slab's pixels of group g
 __global__ void __launch_bounds__(256)
@@ -24,14 +25,10 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   const int C = C1 + C2, cpg = C / GN_GROUPS;
   const int rows_per = (HW + slabs - 1) / slabs;
   const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
-  __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
-  if (threadIdx.x < GN_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  // per-channel partial sums land in shared memory, then one thread per group adds its channels in a fixed
+  // order: no atomics, so the statistics (and everything downstream) are bit-reproducible run to run.
+  __shared__ float s_csum[GN_MAX_C], s_csq[GN_MAX_C];
   const int c2n = C / 2;  // half2 columns
-  // each thread owns a fixed set of half2 columns -> group ids are loop invariant
   for (int cc = threadIdx.x; cc < c2n; cc += blockDim.x) {
     const int c = cc * 2;
     const __half* src;
@@ -45,20 +42,16 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
       s0 += f.x; q0 += f.x * f.x;
       s1 += f.y; q1 += f.y * f.y;
     }
-    const int g0 = c / cpg, g1 = (c + 1) / cpg;
-    if (g0 == g1) {
-      atomicAdd(&s_sum[g0], s0 + s1);
-      atomicAdd(&s_sq[g0], q0 + q1);
-    } else {
-      atomicAdd(&s_sum[g0], s0); atomicAdd(&s_sq[g0], q0);
-      atomicAdd(&s_sum[g1], s1); atomicAdd(&s_sq[g1], q1);
-    }
+    s_csum[c] = s0; s_csq[c] = q0;
+    s_csum[c + 1] = s1; s_csq[c + 1] = q1;
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
+    float s = 0.f, q = 0.f;
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { s += s_csum[c]; q += s_csq[c]; }
     float* o = partial + (((size_t)b * slabs + slab) * GN_GROUPS + threadIdx.x) * 2;
-    o[0] = s_sum[threadIdx.x];
-    o[1] = s_sq[threadIdx.x];
+    o[0] = s;
+    o[1] = q;
   }
 }
 
@@ -111,7 +104,7 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st) {
   const int C = C1 + C2;
-  TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
+  TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C <= GN_MAX_C, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
   TG_CHECK(workspace != nullptr, "groupnorm: workspace (B*64*32*2 floats) required");
   int slabs = HW >= 4096 ? 64 : HW >= 1024 ? 32 : HW >= 256 ? 8 : 2;
   if (slabs > GN_MAX_SLABS) slabs = GN_MAX_SLABS;
