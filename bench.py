@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- denoise-steps/sec of TheaterGen's hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by torch.distributed.run, one rank per GPU)
+
+Workload (BASELINE.json configs[2] / SURVEY.md 8d "config 3", the configuration the metric is quoted on):
+SD-1.5 512x512, 4 characters with layout masks + attention-guidance energy, 50 DDIM steps, CFG 7.5, context =
+77 text + 4 IP-Adapter tokens, seeded synthetic SD-1.5-shaped weights (no checkpoints exist offline).
+One bench "step" is one timestep index of a turn:
+    * the stage-1 denoise step of the 4 co-batched characters (one B=8 UNet forward, per-sample IP scales
+      0.0/0.4/0.4/0.4, fused CFG+DDIM)                                          = 4 denoise steps
+    * the stage-2 denoise step of the composed image (B=2 UNet forward, IP scale 0.1, fused CFG+DDIM+masked
+      composite, capture of the 4 guidance attention maps + guidance energy for index < 30)  = 1 denoise step
+so value = 5 * K / seconds (x ranks; every rank owns independent dialogues -> weak scaling, no data-path
+collective; the UNet/IP weights are NCCL-broadcast from rank 0 once at start-up).
+ControlNet residuals of stage 2 are outside this round's scope and are not computed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_DENOISE_STEP = 1.607e12  # one B=2 UNet forward, 81 context tokens
+KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
+XYWH = [[278, 251, 157, 185], [358, 328, 150, 180], [168, 4, 100, 80], [4, 331, 80, 70]]  # CMIGBench dialogue 4
+WORKLOAD = ("sd15-512x512, 4 characters (stage-1 co-batched B=8, ip_scale 0/0.4/0.4/0.4) + stage-2 composite step "
+            "(B=2, ip_scale 0.1, layout mask, 4-map guidance energy for index<30), 50 DDIM steps, cfg 7.5, "
+            "ctx 77+4 tokens")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# =============================================================================================================
+# reference arm / cpu baseline: the oracle (CPU restatement of the reference's PyTorch path), fp32, all host cores
+# =============================================================================================================
+def cpu_denoise_steps(n_steps, warmup):
+    import torch
+    from oracle import ddim as OD
+    from oracle import unet as OU
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = OU.synth_state_dict(1234)
+    g = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 81, 768, generator=g)
+    sched = OD.DDIM()
+    sched.set_timesteps(50)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + n_steps):
+            t = int(sched.timesteps[i % 50])
+            t0 = time.perf_counter()
+            eps = OU.unet_forward(sd, torch.cat([lat] * 2), t, ctx, ip_scale=0.4)
+            lat = sched.step(OD.cfg(eps, 7.5), t, lat)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total, cores = cpu_denoise_steps(args.steps, args.warmup)
+    v = args.steps / total
+    sample = f"{args.steps} stage-1 denoise steps of ONE character (B=2 UNet fwd + CFG + DDIM), fp32, oracle port on {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "denoise-steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm times a bounded sample: " + sample},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# =============================================================================================================
+# our arm
+# =============================================================================================================
+def build_inputs(torch, dev, K=4):
+    g = torch.Generator().manual_seed(4321)
+    ctx1 = torch.randn(2 * K, 81, 768, generator=g).half()          # rows [0,K) uncond, [K,2K) cond
+    ctx2 = torch.randn(2, 81, 768, generator=g).half()
+    lat1 = torch.randn(K, 4, 64, 64, generator=torch.Generator().manual_seed(7)).half()
+    lat2 = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(8)).half()
+    x0 = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(77))
+    nz = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(78))
+    scale1 = torch.tensor([0.0, 0.4, 0.4, 0.4] * 2, dtype=torch.float32)
+    return ctx1, ctx2, lat1, lat2, x0, nz, scale1
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from theatergen_b200 import _lib, ops, synth
+    from theatergen_b200.engine import DenoiseEngine
+    from theatergen_b200.unet import TGUNet
+    from theatergen_b200.utils.guidance import EnergyPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (ours) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()  # fail loudly if the extension is missing
+
+    # ---- weights: rank 0 generates, NCCL broadcast to the others (the only collective on this path) ----
+    sd = synth.synth_state_dict(dev, 1234, fill=(rank == 0))
+    if world > 1:
+        flat = torch.cat([v.reshape(-1) for v in sd.values()])
+        dist.broadcast(flat, 0)
+        off = 0
+        for k, v in sd.items():
+            sd[k] = flat[off:off + v.numel()].view_as(v)
+            off += v.numel()
+    net = TGUNet(sd, dev)
+    del sd
+    eng = DenoiseEngine(net)
+    K, STEPS = 4, 50
+    ctx1, ctx2, lat1, lat2, x0, nz, scale1 = build_inputs(torch, dev, K)
+    ts, coef = eng.tables(STEPS, 7.5)
+    sched = eng.scheduler
+    frozen_all = torch.cat([lat2.float()] + [sched.add_noise(x0, nz, torch.tensor([int(t)])) for t in sched.timesteps]).half()
+    frozen_all = frozen_all.view(STEPS + 1, 1, 4, 64, 64)
+    mask = torch.zeros(64, 64)
+    for x, y, w, h in XYWH:
+        mask[round(y / 8):round(y / 8) + round(h / 8), round(x / 8):round(x / 8) + round(w / 8)] = 1.0
+    bboxes = [[x / 512, y / 512, (x + w) / 512, (y + h) / 512] for x, y, w, h in XYWH]
+    plan = EnergyPlan(bboxes, [[5, 6], [9], [12, 13, 14], [17]], KEYS, fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0,
+                      bg_weight=4.0)
+
+    # pinned host staging (e2e leg) and device-resident copies (kernel leg)
+    pin = lambda t: t.contiguous().pin_memory()
+    h_ctx1, h_ctx2, h_lat1, h_lat2, h_frozen, h_mask = map(pin, (ctx1, ctx2, lat1, lat2, frozen_all, mask.half()))
+    h_ts, h_coef = pin(ts.cpu()), pin(coef.cpu())
+    h_ts8, h_ts2 = pin(ts.cpu()[:, None].repeat(1, 2 * K)), pin(ts.cpu()[:, None].repeat(1, 2))
+    h_out1 = torch.empty((K, 4, 64, 64), dtype=torch.float16).pin_memory()
+    h_out2 = torch.empty((1, 4, 64, 64), dtype=torch.float16).pin_memory()
+    h_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+    d_frozen, d_ts, d_coef = frozen_all.to(dev), ts, coef
+
+    g1 = eng.step_graph(K, 81, False)
+    loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+    ws = torch.empty((256,), dtype=torch.float32, device=dev)
+    # stage 2: two graphs -- with and without the guidance energy (index < 30)
+    from theatergen_b200.engine import StepGraph
+
+    class Stage2(StepGraph):
+        def __init__(self, energy):
+            super().__init__(eng, 1, 81, True, KEYS)
+            self.energy = energy
+
+        def _body(self):
+            super()._body()
+            if self.energy:
+                plan.run([self.captured[k][0] for k in KEYS], loss, ws)
+
+    g2e, g2 = Stage2(True).capture(), Stage2(False).capture()
+    g1.ctx.copy_(h_ctx1); g1.ip_scale.copy_(scale1); g1.latents.copy_(h_lat1)
+    for g in (g2e, g2):
+        g.ctx.copy_(h_ctx2); g.ip_scale.fill_(0.1); g.latents.copy_(h_lat2); g.mask.copy_(h_mask)
+    torch.cuda.synchronize()
+    launches_per_step = {True: g1.launches_per_step + g2e.launches_per_step,
+                         False: g1.launches_per_step + g2.launches_per_step}
+
+    def step_device(i):
+        """inputs resident in HBM; only device-side work"""
+        idx = i % STEPS
+        g1.t.copy_(d_ts[idx].expand(2 * K)); g1.coef.copy_(d_coef[idx])
+        g1.replay()
+        g = g2e if idx < 30 else g2
+        g.t.copy_(d_ts[idx].expand(2)); g.coef.copy_(d_coef[idx]); g.frozen.copy_(d_frozen[idx + 1])
+        g.replay()
+        if idx == STEPS - 1:  # start the next synthetic trajectory from fresh noise
+            g1.latents.copy_(h_lat1, non_blocking=True)
+            g2e.latents.copy_(h_lat2, non_blocking=True); g2.latents.copy_(h_lat2, non_blocking=True)
+        elif idx == 29:
+            g2.latents.copy_(g2e.latents)
+        return idx < 30
+
+    def step_e2e(i):
+        """public-API view: that step's inputs come from pinned HOST memory, results are read back to the host
+        and the host waits for them (the reference's per-step latents.cpu(), models/pipelines.py:449-453, 835)"""
+        idx = i % STEPS
+        g1.t.copy_(h_ts8[idx], non_blocking=True); g1.coef.copy_(h_coef[idx], non_blocking=True)
+        if idx == 0:
+            g1.ctx.copy_(h_ctx1, non_blocking=True); g1.latents.copy_(h_lat1, non_blocking=True)
+            for g in (g2e, g2):
+                g.ctx.copy_(h_ctx2, non_blocking=True); g.latents.copy_(h_lat2, non_blocking=True)
+                g.mask.copy_(h_mask, non_blocking=True)
+        g1.replay()
+        g = g2e if idx < 30 else g2
+        g.t.copy_(h_ts2[idx], non_blocking=True); g.coef.copy_(h_coef[idx], non_blocking=True)
+        g.frozen.copy_(h_frozen[idx + 1], non_blocking=True)
+        g.replay()
+        if idx == 29:
+            g2.latents.copy_(g2e.latents)
+        h_out1.copy_(g1.trace, non_blocking=True)
+        h_out2.copy_(g.trace, non_blocking=True)
+        if idx < 30:
+            h_loss.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(warm, warm + n):
+            fn(i)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    Kb, Wb = args.steps, max(3, args.warmup)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, Kb, Wb)
+    clocks = sampler.stop() if rank == 0 else None
+    n_energy = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) < 30)
+    gpu_launches = n_energy * launches_per_step[True] + (Kb - n_energy) * launches_per_step[False]
+    ms_e2e = timed(step_e2e, Kb, Wb)
+
+    # ---- roofline leg: every kernel family timed with CUDA events (eager, same shapes, same stream) ----
+    roof, breakdown = None, None
+    if rank == 0:
+        net.ip_scale_per_sample = None
+        for _ in range(2):
+            g1._body()
+        with ops.profile() as rec:
+            for _ in range(3):
+                g1._body()
+        rec.finish()
+        summ = rec.summary()
+        tot = sum(v["ms"] for v in summ.values())
+        breakdown = {k: {"launches_per_fwd": v["launches"] // 3, "ms_per_fwd": round(v["ms"] / 3, 4),
+                         "share": round(v["ms"] / tot, 4), "tflops": round(v["tflops"], 1), "gbs": round(v["gbs"], 1)}
+                     for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+        tf_peak, hbm_peak, src = peaks()
+        roof = {"kernel": top[0], "bound": "tensor", "achieved": round(top[1]["tflops"], 2), "peak": tf_peak,
+                "unit": "TFLOP/s", "frac": round(top[1]["tflops"] / tf_peak, 4), "traffic": None,
+                "peak_source": f"{src} (bf16_tflops_sustained: kernel timed inside a long step)",
+                "avg_launch_us": round(1e3 * top[1]["ms"] / top[1]["launches"], 2),
+                "algorithmic_flops_per_launch": round(top[1]["flops"] / top[1]["launches"]),
+                "launches_timed": top[1]["launches"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        total, cores = cpu_denoise_steps(2, 1)
+        cpu = {"value": 2 / total, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": "2 stage-1 denoise steps of one character (B=2 UNet fwd + CFG + DDIM), fp32 oracle, after 1 warm-up"}
+
+    if rank == 0:
+        denoise_per_step = (K + 1) * world
+        value = denoise_per_step * Kb / (ms_dev * 1e-3)
+        e2e = denoise_per_step * Kb / (ms_e2e * 1e-3)
+        h2d = 8 * 4 + 8 * 4 + 4 * 64 * 64 * 2 + (h_ctx1.numel() + h_ctx2.numel() + h_lat1.numel() + h_lat2.numel() + h_mask.numel()) * 2 // STEPS
+        d2h = (K + 1) * 4 * 64 * 64 * 2 + 4
+        out = {
+            "metric": "denoise-steps/sec", "value": round(value, 2), "unit": "steps/s", "n_gpus": world,
+            "steps": Kb, "warmup": Wb, "ms_per_step": round(ms_dev / Kb, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "denoise_steps_per_bench_step_per_gpu": K + 1,
+                       "l2_policy": "inputs larger than L2 (1.76 GB of weights streamed per forward vs 126 MB L2)",
+                       "cuda_graphs": True, "controlnet": "not computed (out of scope this round)",
+                       "parallelism": f"dp{world} (independent dialogues per rank, weights NCCL-broadcast once)"},
+            "e2e": {"value": round(e2e, 2), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / Kb, 4)},
+            "gpu_launches": int(gpu_launches), "clocks": clocks,
+            "tensor_frac_of_step": round(value / world * FLOPS_PER_DENOISE_STEP / 1e12 / peaks()[0], 4),
+            "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_stage1_B8": breakdown,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ unsigned long long tg_launch_count(void);
 #define TG_ACT_NONE 0
 #define TG_ACT_SILU 1
 #define TG_ACT_GEGLU 2 /* weight rows packed per 64: [32 value | 32 gate]; out has N/2 columns */
+#define TG_ACT_GELU 3  /* exact (erf) GELU, ip_adapter/resampler.py:18 */
 
 /* out[M,N] = act( [A1|A2][M,K] * Wt[N,K]^T + bias[N] + rowbias[m/rows_per_image, N] ) + residual[M,N]
  * tcgen05 tensor-core GEMM (TMA-fed, TMEM accumulators).  A2 may be NULL (K1 == K); bias / rowbias /

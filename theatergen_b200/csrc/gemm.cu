@@ -33,7 +33,7 @@ struct GemmArgs {
   int ldr;
   __half* out;
   int ldc;
-  int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64)
+  int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64), 3 gelu(erf)
   float out_scale;
 };
 
@@ -81,6 +81,9 @@ __device__ __forceinline__ void epilogue_store32(const GemmArgs& g, float (&v)[3
   if (g.act == 1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+  } else if (g.act == 3) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
   }
   if (g.residual) {
     const uint4* rp = reinterpret_cast<const uint4*>(g.residual + (size_t)m * g.ldr + n);

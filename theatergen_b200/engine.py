@@ -1,0 +1,139 @@
+"""DenoiseEngine -- the per-timestep hot loop on one GPU: CFG-batched UNet forward -> fused CFG + DDIM
+(+ masked composite) -> trace, with K co-batched characters (batch 2K, per-sample IP scale) and the whole step
+replayed as a CUDA graph.
+
+Mirrors the two loops of the reference: models/pipelines.py:406-453 (stage 1) and :742-835 (stage 2; the
+ControlNet call is outside this round's scope and its residuals can be injected through TGUNet directly).
+The reference's per-step `latents.cpu()` (pipelines.py:449-453, 835) becomes an asynchronous device->pinned-host
+copy that is only waited for at the end of the trajectory.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .scheduler import DDIMScheduler
+from .unet import TGUNet
+
+
+class StepGraph:
+    """One denoise step for a fixed (K, frozen?) shape, captured once and replayed with new t / coefficients."""
+
+    def __init__(self, engine, K, T, composite, capture_keys=None):
+        dev = engine.device
+        self.K = K
+        self.latents = torch.zeros((K, 4, 64, 64), dtype=torch.float16, device=dev)
+        self.x_in = torch.zeros((2 * K, 4, 64, 64), dtype=torch.float16, device=dev)
+        self.ctx = torch.zeros((2 * K, T, 768), dtype=torch.float16, device=dev)
+        self.ip_scale = torch.zeros((2 * K,), dtype=torch.float32, device=dev)
+        self.t = torch.zeros((2 * K,), dtype=torch.float32, device=dev)
+        self.coef = torch.zeros((8,), dtype=torch.float32, device=dev)
+        self.trace = torch.zeros((K, 4, 64, 64), dtype=torch.float16, device=dev)
+        self.frozen = torch.zeros((K, 4, 64, 64), dtype=torch.float16, device=dev) if composite else None
+        self.mask = torch.zeros((64, 64), dtype=torch.float16, device=dev) if composite else None
+        self.capture_keys = capture_keys
+        self.captured = {} if capture_keys else None
+        self.engine = engine
+        self.graph = None
+        self.launches_per_step = 0
+
+    def _body(self):
+        net = self.engine.unet
+        ops.duplicate_latents(self.latents, self.x_in)
+        eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
+                              save_keys=self.capture_keys, cond_only=True)
+        ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
+                               latents_copy=self.trace)
+
+    def capture(self):
+        from . import _lib
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm up: lazy kernel attribute setup, allocator pools
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = _lib.launch_count() - n0
+        return self
+
+    def replay(self):
+        self.graph.replay()
+
+
+class DenoiseEngine:
+    def __init__(self, unet: TGUNet, scheduler: DDIMScheduler | None = None, use_graphs=True):
+        self.unet = unet
+        self.device = unet.device
+        self.scheduler = scheduler or DDIMScheduler()
+        self.use_graphs = use_graphs
+        self._graphs = {}
+        self._tables = {}
+
+    def tables(self, num_steps, guidance_scale):
+        key = (num_steps, float(guidance_scale))
+        if key not in self._tables:
+            self.scheduler.set_timesteps(num_steps)
+            coef = self.scheduler.coef_table(guidance_scale, self.device)
+            ts = self.scheduler.timesteps.to(self.device, torch.float32)
+            self._tables[key] = (ts, coef)
+        return self._tables[key]
+
+    def step_graph(self, K, T, composite, capture_keys=None):
+        key = (K, T, composite, tuple(capture_keys) if capture_keys else None)
+        if key not in self._graphs:
+            sg = StepGraph(self, K, T, composite, capture_keys)
+            if self.use_graphs:
+                sg.capture()
+            self._graphs[key] = sg
+        return self._graphs[key]
+
+    @torch.no_grad()
+    def denoise(self, latents, ctx, ip_scale, num_steps=50, guidance_scale=7.5, frozen_all=None, frozen_mask=None,
+                frozen_steps=0, trace_host=None, capture_keys=None, on_step=None):
+        """latents [K,4,64,64], ctx [2K,T,768] (rows [0,K) unconditional), ip_scale float[2K] or float.
+        frozen_all [steps+1,K,4,64,64] + frozen_mask [64,64] enable the stage-2 composite for index < frozen_steps.
+        trace_host: optional pinned fp16 [steps+1,K,4,64,64] receiving every step's latents asynchronously.
+        Returns the final latents (device)."""
+        K, T = latents.shape[0], ctx.shape[1]
+        ts, coef = self.tables(num_steps, guidance_scale)
+        composite = frozen_all is not None and frozen_steps > 0
+        sg = self.step_graph(K, T, composite, capture_keys)
+        sg.latents.copy_(latents, non_blocking=True)
+        sg.ctx.copy_(ctx, non_blocking=True)
+        if torch.is_tensor(ip_scale):
+            sg.ip_scale.copy_(ip_scale.to(torch.float32), non_blocking=True)
+        else:
+            sg.ip_scale.fill_(float(ip_scale))
+        if composite:
+            sg.mask.copy_(frozen_mask.to(torch.float16), non_blocking=True)
+        if trace_host is not None:
+            trace_host[0].copy_(sg.latents, non_blocking=True)
+        sg_plain = None
+        for i in range(num_steps):
+            cur = sg
+            if composite and i >= frozen_steps:  # composite only for index < frozen_steps (pipelines.py:833)
+                if sg_plain is None:
+                    sg_plain = self.step_graph(K, T, False, capture_keys)
+                    sg_plain.ctx.copy_(sg.ctx)
+                    sg_plain.ip_scale.copy_(sg.ip_scale)
+                    sg_plain.latents.copy_(sg.latents)
+                cur = sg_plain
+            cur.t.copy_(ts[i].expand(2 * K), non_blocking=True)
+            cur.coef.copy_(coef[i], non_blocking=True)
+            if cur.frozen is not None:
+                cur.frozen.copy_(frozen_all[i + 1], non_blocking=True)
+            if self.use_graphs:
+                cur.replay()
+            else:
+                cur._body()
+            if trace_host is not None:
+                trace_host[i + 1].copy_(cur.trace, non_blocking=True)
+            if on_step is not None:
+                on_step(i, cur)
+        final = (sg_plain or sg).latents
+        return final

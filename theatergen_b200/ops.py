@@ -9,7 +9,52 @@ import torch
 
 from . import _lib
 
-TG_ACT_NONE, TG_ACT_SILU, TG_ACT_GEGLU = 0, 1, 2
+TG_ACT_NONE, TG_ACT_SILU, TG_ACT_GEGLU, TG_ACT_GELU = 0, 1, 2, 3
+
+# ---------------------------------------------------------------------------------------------------------
+# optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream around each op
+# ---------------------------------------------------------------------------------------------------------
+_PROF = None
+
+
+class profile:
+    """with ops.profile() as rec: ...  -> rec.rows = [(kernel, ms, flops, bytes)] after rec.finish()."""
+
+    def __enter__(self):
+        global _PROF
+        self.events = []
+        _PROF = self
+        return self
+
+    def __exit__(self, *a):
+        global _PROF
+        _PROF = None
+
+    def finish(self):
+        torch.cuda.synchronize()
+        self.rows = [(k, s.elapsed_time(e), f, b) for k, s, e, f, b in self.events]
+        return self.rows
+
+    def summary(self):
+        agg = {}
+        for k, ms, f, b in self.rows:
+            a = agg.setdefault(k, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += ms; a[2] += f; a[3] += b
+        return {k: dict(launches=v[0], ms=v[1], tflops=(v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else 0.0,
+                        gbs=(v[3] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else 0.0, flops=v[2], bytes=v[3])
+                for k, v in agg.items()}
+
+
+def _timed(kernel, flops, nbytes, fn):
+    if _PROF is None:
+        return fn()
+    st = torch.cuda.current_stream()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(st)
+    r = fn()
+    e.record(st)
+    _PROF.events.append((kernel, s, e, float(flops), float(nbytes)))
+    return r
 
 
 def _p(t):
@@ -39,10 +84,11 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
     n_out = N // 2 if act == TG_ACT_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
-    rc = _lib.lib().tg_gemm(_p(a), a.stride(0), K1, _p(a2), 0 if a2 is None else a2.stride(0), _p(w), M, N, K,
+    rc = _timed("gemm_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out + (M * N if residual is not None else 0)),
+                lambda: _lib.lib().tg_gemm(_p(a), a.stride(0), K1, _p(a2), 0 if a2 is None else a2.stride(0), _p(w), M, N, K,
                             _p(bias), _p(rowbias), rows_per_image, 0 if rowbias is None else rowbias.stride(0),
                             _p(residual), 0 if residual is None else residual.stride(0), act, float(out_scale),
-                            _p(out), out.stride(0), _stream())
+                            _p(out), out.stride(0), _stream()))
     _lib.check(rc, "tg_gemm")
     return out
 
@@ -56,9 +102,12 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, out_scale=1.0, out=
     if out is None:
         out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x.device)
     res2 = None if residual is None else residual.reshape(B * H * W, -1)
-    rc = _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
+    Mc = B * H * W
+    rc = _timed("gemm_tc_kernel", 2.0 * Mc * Cout * 9 * Cin,
+                2.0 * (Mc * Cin + Cout * 9 * Cin + Mc * Cout + (Mc * Cout if res2 is not None else 0)),
+                lambda: _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
                                0 if rowbias is None else rowbias.stride(0), _p(res2),
-                               0 if res2 is None else res2.stride(0), float(out_scale), _p(out), Cout, _stream())
+                               0 if res2 is None else res2.stride(0), float(out_scale), _p(out), Cout, _stream()))
     _lib.check(rc, "tg_conv3x3")
     return out
 
@@ -84,8 +133,9 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=False, out=None, workspace=
     if out is None:
         out = torch.empty((B, HW, C1 + C2), dtype=torch.float16, device=x1.device)
     ws = workspace if workspace is not None else _gn_workspace(x1.device, B)
-    rc = _lib.lib().tg_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, _p(gamma), _p(beta), float(eps), int(silu), _p(out),
-                                 _p(ws), _stream())
+    rc = _timed("groupnorm", 0, 2.0 * 3 * B * HW * (C1 + C2),
+                lambda: _lib.lib().tg_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, _p(gamma), _p(beta), float(eps), int(silu),
+                                                _p(out), _p(ws), _stream()))
     _lib.check(rc, "tg_groupnorm")
     return out
 
@@ -95,8 +145,9 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     M, Cc = x.shape
     if out is None:
         out = torch.empty((M, Cc), dtype=torch.float16, device=x.device)
-    rc = _lib.lib().tg_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), _p(out), out.stride(0), M, Cc,
-                                 _stream())
+    rc = _timed("layernorm", 0, 4.0 * M * Cc,
+                lambda: _lib.lib().tg_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), float(eps), _p(out),
+                                                out.stride(0), M, Cc, _stream()))
     _lib.check(rc, "tg_layernorm")
     return out
 
@@ -110,8 +161,9 @@ def attention(q, k, v, B, heads, scale=None, out=None):
         scale = d ** -0.5
     if out is None:
         out = torch.empty((B * Nq, heads * d), dtype=torch.float16, device=q.device)
-    rc = _lib.lib().tg_attention(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out), out.stride(0), B,
-                                 heads, Nq, Nk, d, float(scale), _stream())
+    rc = _timed("attn_self_kernel", 4.0 * B * heads * Nq * Nk * d, 2.0 * B * heads * d * (2 * Nq + 2 * Nk),
+                lambda: _lib.lib().tg_attention(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out),
+                                                out.stride(0), B, heads, Nq, Nk, d, float(scale), _stream()))
     _lib.check(rc, "tg_attention")
     return out
 
@@ -128,9 +180,11 @@ def attention_cross_ip(q, kt, vt, ki, vi, B, heads, n_text, n_ip, ip_scale=None,
         assert ip_scale.dtype == torch.float32 and ip_scale.numel() == B and ip_scale.is_cuda
     if out is None:
         out = torch.empty((B * Nq, Cc), dtype=torch.float16, device=q.device)
-    rc = _lib.lib().tg_attention_cross_ip(_p(q), q.stride(0), _p(kt), _p(vt), _p(ki), _p(vi), kt.stride(0), n_text, n_ip,
-                                          _p(ip_scale), _p(add_mask), _p(out), out.stride(0), _p(probs), probs_b0, B,
-                                          heads, Nq, d, float(d ** -0.5), _stream())
+    rc = _timed("attn_cross_ip_kernel", 4.0 * B * heads * Nq * (n_text + n_ip) * d, 2.0 * 2 * B * Nq * Cc,
+                lambda: _lib.lib().tg_attention_cross_ip(_p(q), q.stride(0), _p(kt), _p(vt), _p(ki), _p(vi), kt.stride(0),
+                                                         n_text, n_ip, _p(ip_scale), _p(add_mask), _p(out),
+                                                         out.stride(0), _p(probs), probs_b0, B, heads, Nq, d,
+                                                         float(d ** -0.5), _stream()))
     _lib.check(rc, "tg_attention_cross_ip")
     return out
 
