@@ -27,6 +27,11 @@ int tg_version(void);
 /* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
 unsigned long long tg_launch_count(void);
 
+/* allocate per-device scratch (64 MB split-K workspace) on the CURRENT device; call once before capturing CUDA
+ * graphs.  Done lazily by the first GEMM otherwise.  Scratch is shared by all GEMM calls of the process on that
+ * device: issue them on one stream at a time. */
+int tg_init(void);
+
 /* activation codes of the GEMM epilogue */
 #define TG_ACT_NONE 0
 #define TG_ACT_SILU 1

@@ -19,7 +19,8 @@ def _close(got, ref, atol, rtol):
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 64), (256, 128, 320), (8192, 320, 320),
                                    (2048, 640, 2560), (512, 1280, 1280), (162, 1280, 768), (2, 1280, 320),
-                                   (300, 192, 128)])
+                                   (300, 192, 128), (512, 1280, 11520), (128, 1280, 2560), (2048, 960, 320),
+                                   (1024, 2560, 640), (256, 49920, 768)])
 def test_gemm_plain(M, N, K):
     from theatergen_b200 import ops
     a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
@@ -39,6 +40,18 @@ def test_gemm_epilogues():
     _close(out, ref, 3e-3, 2e-3)
     out = ops.gemm(a, w, bias, act=ops.TG_ACT_SILU)
     _close(out, torch.nn.functional.silu(a.float() @ w.float().t() + bias.float()), 3e-3, 2e-3)
+
+
+def test_gemm_splitk_with_epilogue_is_deterministic():
+    from theatergen_b200 import ops
+    M, N, K = 512, 1280, 5760
+    a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
+    bias, res, rowbias = _rand((N,), 3), _rand((M, N), 4), _rand((8, N), 5)
+    out = ops.gemm(a, w, bias, rowbias=rowbias, rows_per_image=64, residual=res)
+    ref = a.float() @ w.float().t() + bias.float() + rowbias.float().repeat_interleave(64, 0) + res.float()
+    _close(out, ref, 3e-3, 2e-3)
+    for _ in range(3):
+        assert torch.equal(out, ops.gemm(a, w, bias, rowbias=rowbias, rows_per_image=64, residual=res))
 
 
 def test_gemm_two_sources_and_strided_out():

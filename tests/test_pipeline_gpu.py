@@ -1,0 +1,140 @@
+"""The denoise loops through the reference-facing pipeline surface vs the oracle loops, plus size-independent
+properties at the full BASELINE configuration (50 steps, 4 co-batched characters)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeVAE:
+    class config:
+        scaling_factor = 0.18215
+
+    def decode(self, z, return_dict=True):
+        img = z[:, :3].float().repeat_interleave(8, 2).repeat_interleave(8, 3).clamp(-1, 1)
+        return (img,) if not return_dict else type("O", (), {"sample": img})()
+
+
+class FakeImageProcessor:
+    def postprocess(self, image, output_type="pil", do_denormalize=None):
+        from PIL import Image
+        arr = ((image[0] / 2 + 0.5).clamp(0, 1).permute(1, 2, 0).cpu().numpy() * 255).round().astype("uint8")
+        return [Image.fromarray(arr)]
+
+
+class FakePipe:
+    """Everything the stage functions reach through adapter.pipe, with seeded stand-ins for CLIP text / VAE."""
+    vae_scale_factor = 8
+
+    def __init__(self, unet, scheduler):
+        self.unet, self.scheduler, self.vae, self.image_processor = unet, scheduler, FakeVAE(), FakeImageProcessor()
+
+    def to(self, device):
+        return self
+
+    def encode_prompt(self, prompt, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True,
+                      negative_prompt=None, **kw):
+        def emb(s):
+            g = torch.Generator().manual_seed(abs(hash(s)) % (2 ** 31))
+            return torch.randn(1, 77, 768, generator=g).half().cuda()
+        return emb("p:" + str(prompt)), emb("n:" + str(negative_prompt))
+
+
+def _make(seed=1234):
+    from oracle import unet as OU
+    from theatergen_b200.ip_adapter import IPAdapter
+    from theatergen_b200.scheduler import DDIMScheduler
+    from theatergen_b200.unet import TGUNet
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = OU.synth_state_dict(seed)
+    net = TGUNet(sd)
+    adapter = IPAdapter(FakePipe(net, DDIMScheduler()), device="cuda")
+    from oracle import synth
+    adapter.image_proj_model.load_state_dict(synth.fill(synth.image_proj_shapes(), 9))
+    return OU, sd, net, adapter
+
+
+def test_stage1_and_stage2_loops_match_oracle(tmp_path, monkeypatch):
+    import hashlib
+    monkeypatch.setattr("builtins.hash", lambda s: int(hashlib.md5(str(s).encode()).hexdigest()[:8], 16))
+    from oracle import ddim as OD
+    from oracle import resampler as ORS
+    from oracle import synth
+    from theatergen_b200.models import pipelines
+    OU, sd, net, adapter = _make()
+    steps = 6
+    g = torch.Generator().manual_seed(3)
+    lat0 = torch.randn(1, 4, 64, 64, generator=g).half()
+    clip = torch.randn(1, 1024, generator=g).half()
+    out = pipelines.generate_semantic_guidance(
+        "story", 0, "1.5", "a red fox", str(tmp_path) + "/", 0, adapter, None, lat0, None, steps, None, None, None,
+        save_all_latents=True, obj_id=7, have_reffer=1, clip_image_embeds=clip)
+    latents, image, trace = out[0], out[1], out[-1]
+    assert trace.shape == (steps + 1, 1, 4, 64, 64) and latents.shape == (1, 4, 64, 64)
+    # oracle: same embeddings, fp32, on the GPU
+    pe, ne = adapter.pipe.encode_prompt("full-body picture of a red fox", negative_prompt=pipelines.NEGATIVE_SO)
+    ip_sd = {k: v.half().float().cuda() for k, v in synth.fill(synth.image_proj_shapes(), 9).items()}
+    tok = ORS.image_proj(ip_sd, clip.float().cuda())
+    tok0 = ORS.image_proj(ip_sd, torch.zeros_like(clip).float().cuda())
+    ctx = torch.cat([torch.cat([ne.float(), tok0], 1), torch.cat([pe.float(), tok], 1)])
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref, ref_trace = OD.stage1_loop(lambda x, t, c: OU.unet_forward(sd32, x, t, c, ip_scale=0.4), OD.DDIM(),
+                                        lat0.float().cuda(), ctx, num_steps=steps)
+    err = (trace.float().cuda() - ref_trace).abs().amax(dim=(1, 2, 3, 4))
+    print("stage-1 per-step max|latents - oracle|:", [f"{e:.2e}" for e in err.tolist()])
+    assert err.max().item() < 3e-2 and err[1].item() < 1e-2
+    assert torch.equal(trace[-1].cuda(), latents)
+
+    # stage 2 with the masked composite (index < frozen_steps), injected noise tensors
+    from PIL import Image
+    import numpy as np
+    mask_img = Image.fromarray((np.pad(np.ones((200, 160)), ((150, 162), (100, 252))) * 255).astype("uint8"))
+    init, noise, bg = [torch.randn(1, 4, 64, 64, generator=g).half() for _ in range(3)]
+    lat2, _ = pipelines.final_image_generation(
+        "1.5", None, None, None, "two foxes", "blurry", "forest", [None], None, 0, 512, 512, 11, mask_img, None, adapter,
+        None, torch.zeros(steps + 1, 1, 4, 64, 64), None, None, None, steps, 4, clip_image_embeds=clip,
+        stage2_noise=(init, noise, bg))
+    sched = OD.DDIM()
+    sched.set_timesteps(steps)
+    frozen = torch.cat([bg.float()[None], sched.add_noise(init.float(), noise.float(), sched.timesteps).unsqueeze(1)]).cuda()
+    m = np.array(mask_img.resize((64, 64)).convert("L")).astype(np.float32) / 255.0
+    m[m > 0] = 1
+    fm = torch.from_numpy(1 - m).cuda()
+    pe, ne = adapter.pipe.encode_prompt("two foxes", negative_prompt="blurry")
+    ctx2 = torch.cat([torch.cat([ne.float(), tok0], 1), torch.cat([pe.float(), tok], 1)])
+    with torch.no_grad():
+        ref2 = OD.stage2_loop(lambda x, t, c: OU.unet_forward(sd32, x, t, c, ip_scale=0.1), OD.DDIM(), bg.float().cuda(),
+                              ctx2, frozen, fm, 4, num_steps=steps)
+    e2 = (lat2.float() - ref2).abs().max().item()
+    print("stage-2 max|latents - oracle|:", e2)
+    assert e2 < 3e-2
+
+
+def test_full_config_properties():
+    """50 steps, 4 co-batched characters (BASELINE full size): determinism, batch-position independence,
+    composite idempotence."""
+    OU, sd, net, adapter = _make()
+    from theatergen_b200.engine import DenoiseEngine
+    eng = DenoiseEngine(net, adapter.pipe.scheduler)
+    g = torch.Generator().manual_seed(5)
+    K = 4
+    lat = torch.randn(K, 4, 64, 64, generator=g).half().cuda()
+    ctx = torch.randn(2 * K, 81, 768, generator=g).half().cuda()
+    scale = torch.tensor([0.0, 0.4, 0.4, 0.4] * 2, device="cuda")
+    a = eng.denoise(lat, ctx, scale, 50).clone()
+    b = eng.denoise(lat, ctx, scale, 50).clone()
+    assert torch.equal(a, b), "the 50-step trajectory must be bit-reproducible"
+    assert torch.isfinite(a.float()).all() and a.float().std().item() > 0.05
+    # character 2 alone (K=1) == character 2 inside the co-batch
+    one = eng.denoise(lat[2:3], ctx[[2, K + 2]], scale[[2, K + 2]], 50)
+    assert torch.equal(one[0], a[2]), (one[0].float() - a[2].float()).abs().max()
+    # stage-2 composite: with frozen_steps = 50 the masked region ends exactly on the frozen latents
+    frozen = torch.randn(51, 1, 4, 64, 64, generator=g).half().cuda()
+    mask = torch.zeros(64, 64, device="cuda")
+    mask[10:40, 20:50] = 1
+    out = eng.denoise(lat[:1], ctx[[0, K]], 0.1, 50, frozen_all=frozen, frozen_mask=mask, frozen_steps=50)
+    assert torch.equal(out[0][:, mask.bool()], frozen[50, 0][:, mask.bool()])
+    out30 = eng.denoise(lat[:1], ctx[[0, K]], 0.1, 50, frozen_all=frozen, frozen_mask=mask, frozen_steps=30)
+    assert not torch.equal(out30[0][:, mask.bool()], frozen[50, 0][:, mask.bool()])

@@ -17,6 +17,7 @@ _SIGS = {
     "tg_last_error": (C.c_char_p, []),
     "tg_version": (ci, []),
     "tg_launch_count": (C.c_ulonglong, []),
+    "tg_init": (ci, []),
     "tg_gemm": (ci, [vp, ci, ci, vp, ci, vp, ci, ci, ci, vp, vp, ci, ci, vp, ci, ci, cf, vp, ci, vp]),
     "tg_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, cf, vp, ci, vp]),
     "tg_groupnorm": (ci, [vp, ci, vp, ci, ci, ci, vp, vp, cf, ci, vp, vp, vp]),

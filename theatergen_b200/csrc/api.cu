@@ -13,6 +13,7 @@ extern "C" {
 const char* tg_last_error(void) { return tg::get_error(); }
 int tg_version(void) { return 100; }
 unsigned long long tg_launch_count(void) { return tg::g_launch_count; }
+int tg_init(void) { return tg::gemm_init(); }
 
 int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, const tg_half* Wt, int M, int N,
             int K, const tg_half* bias, const tg_half* rowbias, int rows_per_image, int rowbias_ld,

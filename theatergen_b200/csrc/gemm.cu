@@ -1,4 +1,4 @@
-// tcgen05 + TMA GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+// tcgen05 + TMA GEMM / implicit-GEMM 3x3 convolution for sm_100a (persistent, warp-specialised, split-K).
 //
 //   out[M,N] = epilogue( A[M,K] * Wt[N,K]^T )        fp16 operands, fp32 accumulate in TMEM, fp16 out
 //
@@ -9,8 +9,14 @@
 //            the TMA unit -> the conv padding costs nothing and no im2col buffer exists.
 // Both land in shared memory as the canonical K-major SWIZZLE_128B layout that tcgen05.mma consumes.
 //
-// Roles (192 threads): warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer,
-// warps2..5 = epilogue (TMEM -> registers -> fused bias/temb/residual/activation -> global).
+// One CTA per SM loops over work items (128 x BN output tile, K-split); N fastest so co-running CTAs share A
+// rows in L2.  Roles (192 threads): warp0 = TMA producer (STAGES-deep smem ring), warp1 = TMEM allocator +
+// single-thread tcgen05.mma issuer, warps2..5 = epilogue.  The accumulator is double-buffered in TMEM
+// (2 x BN columns), so the epilogue of item i (TMEM -> registers -> bias/temb/activation/residual -> swizzled
+// smem -> TMA store) overlaps the main loop of item i+1.
+// Split-K (small-M, long-K layers: the 8x8 / 16x16 levels stream 30-60 MB of weights through <= 40 tiles):
+// every split writes its fp32 partial tile to an L2-resident workspace, a per-tile semaphore elects the last
+// arriving CTA, which sums the partials in a FIXED order (bit-reproducible) and runs the fused epilogue.
 // Replaces, for the hot path, every cuBLAS/cuDNN call the reference issues through
 // nn.Linear / nn.Conv2d (reference: ip_adapter/attention_processor.py:333-359,461-520,
 // ip_adapter/attention.py:269-367, ip_adapter/transformer_2d.py:288-342, diffusers ResnetBlock2D).
@@ -21,6 +27,12 @@ namespace tg {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
+static constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, alternating column chunks
+static constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 64 fp16 per warp per buffer
+static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+static constexpr int MAX_SPLIT = 8;
+static constexpr size_t SPLITK_WS_BYTES = (size_t)64 << 20;
+static constexpr int SPLITK_MAX_TILES = 4096;
 
 struct GemmArgs {
   int M, N, K, K1;
@@ -31,10 +43,11 @@ struct GemmArgs {
   int rows_per_image, rowbias_ld;
   const __half* residual;
   int ldr;
-  __half* out;
-  int ldc;
   int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64), 3 gelu(erf)
   float out_scale;
+  int num_m, num_n, splits;
+  float* ws;   // split-K partials: [tile][split][BN/4][128][4] fp32
+  int* sem;    // split-K arrival counters, one per tile (self-resetting)
 };
 
 template <int BN, int STAGES>
@@ -42,102 +55,122 @@ struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_BUF_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 32 + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ void epilogue_store32(const GemmArgs& g, float (&v)[32], int m, int n, bool row_ok) {
-  // v: 32 consecutive output columns [n, n+32) of row m (already scaled / activated except bias etc.)
-  if (g.bias) {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void add_h8(float* v, uint4 b) {
+  const __half2* h = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    v[2 * j] += f.x;
+    v[2 * j + 1] += f.y;
+  }
+}
+
+// EC (64 or 32) output columns of one row: bias / temb / activation / residual, then fp16 into the swizzled staging
+// buffer (row pitch EC*2 bytes; SWIZZLE_128B for EC = 64, SWIZZLE_64B for EC = 32 -- must match the C tensor map).
+template <int EC>
+__device__ __forceinline__ void epilogue_row(const GemmArgs& g, float (&v)[EC], const uint4 (&res)[EC / 8], int m, int n,
+                                             bool row_ok, uint8_t* stage_row, int row_in_warp) {
+  if (g.bias && g.act != 2) {
     const uint4* bp = reinterpret_cast<const uint4*>(g.bias + n);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 b = __ldg(bp + i);
-      const __half2* h = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __half22float2(h[j]);
-        v[i * 8 + j * 2] += f.x;
-        v[i * 8 + j * 2 + 1] += f.y;
-      }
-    }
+    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], __ldg(bp + i));
   }
-  if (!row_ok) return;
-  if (g.rowbias) {
-    const uint4* bp =
-        reinterpret_cast<const uint4*>(g.rowbias + (size_t)(m / g.rows_per_image) * g.rowbias_ld + n);
+  if (row_ok && g.rowbias) {
+    const uint4* bp = reinterpret_cast<const uint4*>(g.rowbias + (size_t)(m / g.rows_per_image) * g.rowbias_ld + n);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 b = __ldg(bp + i);
-      const __half2* h = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __half22float2(h[j]);
-        v[i * 8 + j * 2] += f.x;
-        v[i * 8 + j * 2 + 1] += f.y;
-      }
-    }
+    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], __ldg(bp + i));
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    for (int i = 0; i < EC; ++i) v[i] = silu_f(v[i]);
   } else if (g.act == 3) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
+    for (int i = 0; i < EC; ++i) v[i] = gelu_erf_f(v[i]);
   }
-  if (g.residual) {
-    const uint4* rp = reinterpret_cast<const uint4*>(g.residual + (size_t)m * g.ldr + n);
+  if (row_ok && g.residual) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 b = __ldg(rp + i);
-      const __half2* h = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __half22float2(h[j]);
-        v[i * 8 + j * 2] += f.x;
-        v[i * 8 + j * 2 + 1] += f.y;
-      }
-    }
+    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], res[i]);
   }
-  uint4* op = reinterpret_cast<uint4*>(g.out + (size_t)m * g.ldc + n);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < EC / 8; ++i) {
     uint4 o;
     __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       h[j] = __floats2half2_rn(v[i * 8 + j * 2] * g.out_scale, v[i * 8 + j * 2 + 1] * g.out_scale);
-    op[i] = o;
+    // 16-byte chunk i of row r lives at chunk (i ^ (r & 7)) [128B swizzle] / (i ^ ((r >> 1) & 3)) [64B swizzle]
+    const int sw = EC == 64 ? (i ^ (row_in_warp & 7)) : (i ^ ((row_in_warp >> 1) & 3));
+    *reinterpret_cast<uint4*>(stage_row + (sw << 4)) = o;
+  }
+}
+
+// residual prefetch: issued before the accumulator wait so the global latency overlaps it
+template <int EC>
+__device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[EC / 8], int m, int n, bool row_ok) {
+  if (row_ok && g.residual) {
+    const uint4* rp = reinterpret_cast<const uint4*>(g.residual + (size_t)m * g.ldr + n);
+#pragma unroll
+    for (int i = 0; i < EC / 8; ++i) res[i] = __ldg(rp + i);
   }
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
   using L = GemmSmem<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = empty_bar + STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int nk = g.K / BK;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  const int S = g.splits;
+  const int num_work = g.num_m * g.num_n * S;
+  constexpr uint32_t ACC_STRIDE = BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -152,118 +185,226 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int conv_b0 = 0, conv_y0 = 0, cblk = 1;
-      if (g.mode == 1) {
-        const int hw = g.H * g.W;
-        conv_b0 = m0 / hw;
-        conv_y0 = (m0 % hw) / g.W;
-        cblk = g.Cin / BK;
-      }
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if (g.mode == 0) {
-          const int k0 = it * BK;
-          if (k0 < g.K1)
-            tma_load_2d(sa, &tmA1, &full_bar[s], k0, m0);
-          else
-            tma_load_2d(sa, &tmA2, &full_bar[s], k0 - g.K1, m0);
-        } else {
-          const int tap = it / cblk;
-          const int c0 = (it - tap * cblk) * BK;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          tma_load_4d(sa, &tmA1, &full_bar[s], c0, kx - 1, conv_y0 + ky - 1, conv_b0);
+      int it = 0;  // k-iteration counter across work items (ring position)
+      const int hw = g.H * g.W;
+      const int cblk = g.mode == 1 ? g.Cin / BK : 1;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / S, split = w - tile * S;
+        const int m0 = (tile / g.num_n) * BM, n0 = (tile % g.num_n) * BN;
+        const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
+        int conv_b0 = 0, conv_y0 = 0;
+        if (g.mode == 1) {
+          conv_b0 = m0 / hw;
+          conv_y0 = (m0 % hw) / g.W;
         }
-        tma_load_2d(sb, &tmB, &full_bar[s], it * BK, n0);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (g.mode == 0) {
+            const int k0 = kb * BK;
+            if (k0 < g.K1)
+              tma_load_2d(sa, &tmA1, &full_bar[s], k0, m0);
+            else
+              tma_load_2d(sa, &tmA2, &full_bar[s], k0 - g.K1, m0);
+          } else {
+            const int tap = kb / cblk;
+            const int c0 = (kb - tap * cblk) * BK;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(sa, &tmA1, &full_bar[s], c0, kx - 1, conv_y0 + ky - 1, conv_b0);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, j = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++j) {
+        const int tile = w / S, split = w - tile * S;
+        const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
+        const int as = j & 1;
+        mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + L::A_BYTES;
+        const uint32_t d_addr = tmem_base + as * ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
-          umma_f16_ss(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
+            umma_f16_ss(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        tc_commit(&acc_full[as]);  // accumulator complete
       }
-      tc_commit(accum_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue warps =====
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < g.M;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (g.act != 2) {
+    // warp (2 + e): TMEM lane quarter q = warp & 3 (hardware rule), column-chunk parity half = e >> 2
+    constexpr int EC = (BN % 64 == 0) ? 64 : 32;
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int row_in_tile = q * 32 + lane;
+    uint8_t* my_stage = smem + L::EPI_OFFSET + e * EPI_BUF_BYTES;  // one staging buffer per epilogue warp
+    int j = 0, chunk_ctr = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++j) {
+      const int tile = w / S, split = w - tile * S;
+      const int m0 = (tile / g.num_n) * BM, n0 = (tile % g.num_n) * BN;
+      const int as = j & 1;
+      const int m = m0 + row_in_tile;
+      const bool row_ok = m < g.M;
+      const uint32_t lane_addr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+
+      if (S > 1) {
+        // ---- split-K: spill the fp32 partial tile, elect the last arriving CTA of this tile ----
+        mbar_wait(&acc_full[as], (j >> 1) & 1);
+        tc_fence_after();
+        float4* wsp = reinterpret_cast<float4*>(g.ws) + ((size_t)(tile * S + split) * (BN / 4)) * BM + row_in_tile;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_addr + c, r);
-        tmem_ld_wait();
-        float v[32];
+        for (int c = half * 32; c < BN; c += 64) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(lane_addr + c, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        epilogue_store32(g, v, m, n0 + c, row_ok);
-      }
-    } else {
-      // GEGLU: per 64 packed columns -> 32 outputs value*gelu(gate); bias is packed the same way
+          for (int i = 0; i < 8; ++i)
+            __stcg(wsp + (size_t)(c / 4 + i) * BM,
+                   make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);  // accumulator is free again
+        __threadfence();
+        epi_bar_sync();
+        if (threadIdx.x == 64) {
+          const int old = atomicAdd(g.sem + tile, 1);
+          const int last = old == S - 1;
+          if (last) g.sem[tile] = 0;  // self-reset: every split of this tile has arrived
+          *last_flag = last;
+        }
+        epi_bar_sync();
+        const bool is_last = *last_flag != 0;
+        epi_bar_sync();  // everyone has read the flag before the next item may overwrite it
+        if (!is_last) continue;
+        __threadfence();
+        const float4* rsp = reinterpret_cast<const float4*>(g.ws) + ((size_t)tile * S * (BN / 4)) * BM + row_in_tile;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {
-        uint32_t ra[32], rg[32];
-        tmem_ld_32x32b_x32(lane_addr + c, ra);
-        tmem_ld_32x32b_x32(lane_addr + c + 32, rg);
-        tmem_ld_wait();
-        float v[32];
-        const uint4* bpa = reinterpret_cast<const uint4*>(g.bias + n0 + c);
-        const uint4* bpg = reinterpret_cast<const uint4*>(g.bias + n0 + c + 32);
+        for (int c = half * EC; c < BN; c += 2 * EC, ++chunk_ctr) {
+          uint8_t* buf = my_stage;
+          uint4 res[EC / 8];
+          load_residual<EC>(g, res, m, n0 + c, row_ok);
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+          float v[EC];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 ba = __ldg(bpa + i), bg = __ldg(bpg + i);
-          const __half2* ha = reinterpret_cast<const __half2*>(&ba);
-          const __half2* hg = reinterpret_cast<const __half2*>(&bg);
+          for (int i = 0; i < EC; ++i) v[i] = 0.f;
+          for (int s = 0; s < S; ++s) {  // fixed summation order -> deterministic
+            const float4* p = rsp + ((size_t)s * (BN / 4) + c / 4) * BM;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 fa = __half22float2(ha[j]), fg = __half22float2(hg[j]);
-            const int e = i * 8 + j * 2;
-            // the reference rounds both halves of the projection to fp16 before the gated product
-            // (ip_adapter/attention.py:359-367); keep that rounding so GELU sees the same gate
-            float a0 = __half2float(__float2half_rn(__uint_as_float(ra[e]) + fa.x));
-            float a1 = __half2float(__float2half_rn(__uint_as_float(ra[e + 1]) + fa.y));
-            float g0 = __half2float(__float2half_rn(__uint_as_float(rg[e]) + fg.x));
-            float g1 = __half2float(__float2half_rn(__uint_as_float(rg[e + 1]) + fg.y));
-            v[e] = a0 * gelu_erf_f(g0);
-            v[e + 1] = a1 * gelu_erf_f(g1);
+            for (int i = 0; i < EC / 4; ++i) {
+              const float4 f = __ldcg(p + (size_t)i * BM);
+              v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+            }
+          }
+          epilogue_row<EC>(g, v, res, m, n0 + c, row_ok, buf + lane * (EC * 2), lane);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, buf, n0 + c, m0 + q * 32);
+            bulk_commit();
           }
         }
-        if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(g.out + (size_t)m * g.ldc + (n0 + c) / 2);
+        continue;
+      }
+
+      const int step = g.act == 2 ? 2 * EC : EC;  // accumulator columns consumed per EC output columns
+      bool waited = false;
+#pragma unroll 1
+      for (int c = half * step; c < BN; c += 2 * step, ++chunk_ctr) {
+        uint8_t* buf = my_stage;
+        const int n_out = g.act == 2 ? (n0 + c) >> 1 : n0 + c;
+        uint4 res[EC / 8];
+        load_residual<EC>(g, res, m, n_out, row_ok);
+        if (!waited) {
+          mbar_wait(&acc_full[as], (j >> 1) & 1);
+          tc_fence_after();
+          waited = true;
+        }
+        // the TMA store that last read this warp's staging buffer must have finished reading it
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+        float v[EC];
+        if (g.act != 2) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            __half2* h = reinterpret_cast<__half2*>(&o);
+          for (int h2 = 0; h2 < EC / 32; ++h2) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(lane_addr + c + h2 * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[i * 8 + j * 2], v[i * 8 + j * 2 + 1]);
-            op[i] = o;
+            for (int i = 0; i < 32; ++i) v[h2 * 32 + i] = __uint_as_float(r[i]);
+          }
+        } else {
+          // GEGLU: accumulator columns packed per 64 as [32 value | 32 gate]; bias packed the same way.  The
+          // reference rounds both halves of the projection to fp16 before the gated product
+          // (ip_adapter/attention.py:359-367): keep that rounding so GELU sees the same gate.
+#pragma unroll
+          for (int hlf = 0; hlf < EC / 32; ++hlf) {
+            uint32_t ra[32], rg[32];
+            tmem_ld_32x32b_x32(lane_addr + c + hlf * 64, ra);
+            tmem_ld_32x32b_x32(lane_addr + c + hlf * 64 + 32, rg);
+            tmem_ld_wait();
+            const uint4* bpa = reinterpret_cast<const uint4*>(g.bias + n0 + c + hlf * 64);
+            const uint4* bpg = bpa + 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 ba = __ldg(bpa + i), bg = __ldg(bpg + i);
+              const __half2* ha = reinterpret_cast<const __half2*>(&ba);
+              const __half2* hg = reinterpret_cast<const __half2*>(&bg);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float2 fa = __half22float2(ha[jj]), fg = __half22float2(hg[jj]);
+                const int ee = i * 8 + jj * 2;
+                const float a0 = __half2float(__float2half_rn(__uint_as_float(ra[ee]) + fa.x));
+                const float a1 = __half2float(__float2half_rn(__uint_as_float(ra[ee + 1]) + fa.y));
+                const float g0 = __half2float(__float2half_rn(__uint_as_float(rg[ee]) + fg.x));
+                const float g1 = __half2float(__float2half_rn(__uint_as_float(rg[ee + 1]) + fg.y));
+                v[hlf * 32 + ee] = a0 * gelu_erf_f(g0);
+                v[hlf * 32 + ee + 1] = a1 * gelu_erf_f(g1);
+              }
+            }
           }
         }
+        epilogue_row<EC>(g, v, res, m, n_out, row_ok, buf + lane * (EC * 2), lane);
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, buf, n_out, m0 + q * 32);  // rows >= M are clipped by the tensor map
+          bulk_commit();
+        }
       }
+      if (!waited) {  // this warp had no chunk in this tile (narrow tile): still has to observe the phase
+        mbar_wait(&acc_full[as], (j >> 1) & 1);
+        tc_fence_after();
+      }
+      // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if (lane == 0) bulk_wait<0>();
     tc_fence_before();
   }
   __syncthreads();
@@ -274,9 +415,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+struct DeviceScratch {
+  float* ws = nullptr;
+  int* sem = nullptr;
+  int num_sms = 0;
+};
+static DeviceScratch g_scratch[16];
+
+static int get_scratch(DeviceScratch** out) {
+  int dev = 0;
+  TG_CUDA(cudaGetDevice(&dev));
+  TG_CHECK(dev >= 0 && dev < 16, "device index %d out of range", dev);
+  DeviceScratch& s = g_scratch[dev];
+  if (s.ws == nullptr) {
+    // allocated once per device, outside any stream capture (every captured path is warmed up eagerly first)
+    TG_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    TG_CUDA(cudaMalloc(&s.ws, SPLITK_WS_BYTES));
+    TG_CUDA(cudaMalloc(&s.sem, SPLITK_MAX_TILES * sizeof(int)));
+    TG_CUDA(cudaMemset(s.sem, 0, SPLITK_MAX_TILES * sizeof(int)));
+  }
+  *out = &s;
+  return 0;
+}
+
+int gemm_init() {
+  DeviceScratch* s;
+  return get_scratch(&s);
+}
+
 template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmArgs& g,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
+                       GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, STAGES>;
@@ -284,21 +456,82 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const CUten
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
-  dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
-  kern<<<grid, 192, L::TOTAL, st>>>(a1, a2, b, g);
+  CUtensorMap b;
+  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, BN)) return -1;
+  const int work = g.num_m * g.num_n * g.splits;
+  kern<<<work < sc.num_sms ? work : sc.num_sms, NUM_THREADS, L::TOTAL, st>>>(a1, a2, b, c, g);
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
 }
 
-static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, const GemmArgs& g, const __half* Wt,
+// Tile width / split choice: minimise   waves(work items over 148 SMs) x (k-blocks per item x per-k-block cost
+// + epilogue).  Per k-block (128 x BN x 64): tensor pipe 2*BN cycles, smem->tensor feed (16 KB + 128*BN B) at
+// 128 B/clk = 128 + BN cycles.  Wider tiles raise flop/byte; split-K fills the SMs when M is small and K long.
+static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out) {
+  const int num_m = (M + BM - 1) / BM, nk = K / BK;
+  const int cands[5] = {256, 192, 160, 128, 64};
+  double best_cost = 1e30;
+  *bn_out = 64;
+  *split_out = 1;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    if (N % bn) continue;
+    if (act == 2 && bn % 128) continue;
+    const int tiles = num_m * (N / bn);
+    int s = 1;
+    if (act != 2 && tiles * 2 <= num_sms && nk >= 16) {
+      s = num_sms / tiles;
+      if (s > MAX_SPLIT) s = MAX_SPLIT;
+      if (s > nk / 8) s = nk / 8;
+      if (s < 1) s = 1;
+      while (s > 1 && ((size_t)tiles * s * BM * bn * 4 > SPLITK_WS_BYTES || tiles > SPLITK_MAX_TILES)) --s;
+    }
+    const int waves = (tiles * s + num_sms - 1) / num_sms;
+    const double per_kb = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
+    const double epi = 400.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
+    const double cost = waves * (per_kb * ((nk + s - 1) / s) + epi);
+    if (cost < best_cost * 0.999) {
+      best_cost = cost;
+      *bn_out = bn;
+      *split_out = s;
+    }
+  }
+}
+
+static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, const __half* Wt, __half* out, int ldc,
                     cudaStream_t st) {
-  int bn = (g.N % 128 == 0) ? 128 : 64;
-  if (g.act == 2) TG_CHECK(g.N % 64 == 0 && g.bias != nullptr, "geglu epilogue needs N%%64==0 and a bias");
-  CUtensorMap b;
-  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, bn)) return -1;
-  if (bn == 128) return launch_gemm<128, 3>(a1, a2, b, g, st);
-  return launch_gemm<64, 4>(a1, a2, b, g, st);
+  if (g.act == 2) TG_CHECK(g.N % 128 == 0 && g.bias != nullptr, "geglu epilogue needs N%%128==0 and a bias");
+  DeviceScratch* sc;
+  if (get_scratch(&sc)) return -1;
+  const int n_out = g.act == 2 ? g.N / 2 : g.N;
+  int bn, splits;
+  pick_tile(g.M, g.N, g.K, g.act, sc->num_sms, &bn, &splits);
+  CUtensorMap c;  // epilogue chunks: 64 columns (128B swizzle) or, for BN = 160, 32 columns (64B swizzle)
+  if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, bn % 64 == 0 ? 64 : 32)) return -1;
+  g.num_m = (g.M + BM - 1) / BM;
+  g.num_n = g.N / bn;
+  g.splits = splits;
+  g.ws = sc->ws;
+  g.sem = sc->sem;
+  switch (bn) {
+    case 256: return launch_gemm<256, 4>(a1, a2, Wt, c, g, *sc, st);
+    case 192: return launch_gemm<192, 4>(a1, a2, Wt, c, g, *sc, st);
+    case 160: return launch_gemm<160, 5>(a1, a2, Wt, c, g, *sc, st);
+    case 128: return launch_gemm<128, 6>(a1, a2, Wt, c, g, *sc, st);
+    default: return launch_gemm<64, 8>(a1, a2, Wt, c, g, *sc, st);
+  }
+}
+
+static void fill_args(GemmArgs& g, const EpilogueSpec& e) {
+  g.bias = e.bias;
+  g.rowbias = e.rowbias;
+  g.rows_per_image = e.rows_per_image > 0 ? e.rows_per_image : 1;
+  g.rowbias_ld = e.rowbias_ld;
+  g.residual = e.residual;
+  g.ldr = e.ldr;
+  g.act = e.act;
+  g.out_scale = e.out_scale;
 }
 
 int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, const __half* Wt, int M, int N,
@@ -308,9 +541,7 @@ int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, 
   TG_CHECK(A2 != nullptr || K1 == K, "gemm: K1<K needs a second A source");
   GemmArgs g{};
   g.M = M; g.N = N; g.K = K; g.K1 = K1; g.mode = 0;
-  g.bias = e.bias; g.rowbias = e.rowbias; g.rows_per_image = e.rows_per_image > 0 ? e.rows_per_image : 1;
-  g.rowbias_ld = e.rowbias_ld; g.residual = e.residual; g.ldr = e.ldr; g.out = out; g.ldc = ldc; g.act = e.act;
-  g.out_scale = e.out_scale;
+  fill_args(g, e);
   CUtensorMap a1, a2;
   if (make_tmap_2d(&a1, A1, M, K1, lda1, BM)) return -1;
   if (K1 < K) {
@@ -318,7 +549,7 @@ int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, 
   } else {
     a2 = a1;
   }
-  return dispatch(a1, a2, g, Wt, st);
+  return dispatch(a1, a2, g, Wt, out, ldc, st);
 }
 
 int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, const EpilogueSpec& e,
@@ -335,12 +566,10 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
   GemmArgs g{};
   g.M = B * H * W; g.N = Cout; g.K = 9 * Cin; g.K1 = g.K; g.mode = 1;
   g.H = H; g.W = W; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
-  g.bias = e.bias; g.rowbias = e.rowbias; g.rows_per_image = e.rows_per_image > 0 ? e.rows_per_image : 1;
-  g.rowbias_ld = e.rowbias_ld; g.residual = e.residual; g.ldr = e.ldr; g.out = out; g.ldc = ldc; g.act = e.act;
-  g.out_scale = e.out_scale;
+  fill_args(g, e);
   CUtensorMap a1;
   if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, W)) return -1;
-  return dispatch(a1, a1, g, Wt, st);
+  return dispatch(a1, a1, g, Wt, out, ldc, st);
 }
 
 }  // namespace tg

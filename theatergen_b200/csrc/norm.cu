@@ -15,53 +15,82 @@ namespace tg {
 
 static constexpr int GN_GROUPS = 32;
 static constexpr int GN_MAX_SLABS = 64;
-static constexpr int GN_MAX_C = 2560;
+static constexpr int GN_THREADS = 320;  // >= C/8 for C <= 2560
+static constexpr int GN_VEC = 4;
 
-// partial[b][slab][g][2] = (sum, sumsq) over the slab's pixels of group g
-__global__ void __launch_bounds__(256)
+// partial[b][slab][g][2] = (sum, sumsq) over the slab's pixels of group g.
+// Thread (r, chunk) owns one 16-byte column chunk (8 channels) and walks rows r, r+R, ... of the slab with four
+// independent 16-byte loads in flight; row-lanes are then combined through shared memory in a fixed order and one
+// thread per group adds its channels in a fixed order: no atomics -> bit-reproducible statistics.
+__global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
                 float* __restrict__ partial) {
   const int b = blockIdx.y, slab = blockIdx.x;
-  const int C = C1 + C2, cpg = C / GN_GROUPS;
+  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
   const int rows_per = (HW + slabs - 1) / slabs;
   const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
-  // per-channel partial sums land in shared memory, then one thread per group adds its channels in a fixed
-  // order: no atomics, so the statistics (and everything downstream) are bit-reproducible run to run.
-  __shared__ float s_csum[GN_MAX_C], s_csq[GN_MAX_C];
-  const int c2n = C / 2;  // half2 columns
-  for (int cc = threadIdx.x; cc < c2n; cc += blockDim.x) {
-    const int c = cc * 2;
+  const int R = GN_THREADS / c8n;  // row lanes (>= 1 because c8n <= GN_THREADS)
+  extern __shared__ float s_gn[];  // [R][C] sums, then [R][C] sumsq
+  float* s_sum = s_gn;
+  float* s_sq = s_gn + R * C;
+  const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  if (rl < R) {
+    const int c = chunk * 8;
     const __half* src;
-    int ld, cs;
-    if (c < C1) { src = x1; ld = C1; cs = c; } else { src = x2; ld = C2; cs = c - C1; }
-    const __half* p = src + ((size_t)b * HW + r0) * ld + cs;
-    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r, p += ld) {
-      float2 f = __half22float2(*reinterpret_cast<const __half2*>(p));
-      s0 += f.x; q0 += f.x * f.x;
-      s1 += f.y; q1 += f.y * f.y;
+    int ld;
+    if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
+    src += (size_t)b * HW * ld;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    int r = r0 + rl;
+    for (; r + 3 * R < r1; r += 4 * R) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+          s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+        }
+      }
     }
-    s_csum[c] = s0; s_csq[c] = q0;
-    s_csum[c + 1] = s1; s_csq[c + 1] = q1;
+    for (; r < r1; r += R) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_sum[rl * C + c + j] = s[j];
+      s_sq[rl * C + c + j] = q[j];
+    }
   }
   __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
     float s = 0.f, q = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) { s += s_csum[c]; q += s_csq[c]; }
+    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
+      for (int k = 0; k < R; ++k) { s += s_sum[k * C + c]; q += s_sq[k * C + c]; }
     float* o = partial + (((size_t)b * slabs + slab) * GN_GROUPS + threadIdx.x) * 2;
     o[0] = s;
     o[1] = q;
   }
 }
 
-// Coalescing note for gn_stats_kernel: consecutive threads read consecutive half2 of the same pixel row, so a
-// warp reads 128 contiguous bytes per row step.
-
+// normalise (+SiLU): every thread handles GN_VEC 16-byte vectors, all loads issued before any math
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
                 const float* __restrict__ partial, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, float eps, int silu, __half* __restrict__ out, int rows_per_cta) {
+                const __half* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
   const int b = blockIdx.y;
   const int C = C1 + C2, cpg = C / GN_GROUPS;
   __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -76,16 +105,30 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     s_rstd[threadIdx.x] = rsqrtf(var + eps);
   }
   __syncthreads();
-  const int r0 = blockIdx.x * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-  const int c8n = C / 8;  // 16-byte vectors per row (C1, C2 are multiples of 8)
-  const int total = (r1 - r0) * c8n;
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + i / c8n, c = (i % c8n) * 8;
-    const __half* src = (c < C1) ? x1 + ((size_t)b * HW + r) * C1 + c : x2 + ((size_t)b * HW + r) * C2 + (c - C1);
-    uint4 v = *reinterpret_cast<const uint4*>(src);
-    uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + c));
-    uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + c));
-    const __half* hv = reinterpret_cast<const __half*>(&v);
+  const int c8n = C / 8;
+  const int total = HW * c8n;
+  const int base = blockIdx.x * (256 * GN_VEC) + threadIdx.x;
+  uint4 v[GN_VEC];
+  int cc[GN_VEC], rr[GN_VEC];
+#pragma unroll
+  for (int u = 0; u < GN_VEC; ++u) {
+    const int i = base + u * 256;
+    if (i < total) {
+      rr[u] = i / c8n;
+      cc[u] = (i - rr[u] * c8n) * 8;
+      const __half* src = (cc[u] < C1) ? x1 + ((size_t)b * HW + rr[u]) * C1 + cc[u]
+                                       : x2 + ((size_t)b * HW + rr[u]) * C2 + (cc[u] - C1);
+      v[u] = *reinterpret_cast<const uint4*>(src);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < GN_VEC; ++u) {
+    const int i = base + u * 256;
+    if (i >= total) continue;
+    const int c = cc[u];
+    const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+    const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + c));
+    const __half* hv = reinterpret_cast<const __half*>(&v[u]);
     const __half* hg = reinterpret_cast<const __half*>(&gm);
     const __half* hb = reinterpret_cast<const __half*>(&bt);
     uint4 o;
@@ -97,26 +140,32 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
       if (silu) y = silu_f(y);
       ho[j] = __float2half_rn(y);
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + r) * C + c) = o;
+    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + rr[u]) * C + c) = o;
   }
 }
 
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st) {
   const int C = C1 + C2;
-  TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C <= GN_MAX_C, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
+  TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN_THREADS, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
   TG_CHECK(workspace != nullptr, "groupnorm: workspace (B*64*32*2 floats) required");
-  int slabs = HW >= 4096 ? 64 : HW >= 1024 ? 32 : HW >= 256 ? 8 : 2;
-  if (slabs > GN_MAX_SLABS) slabs = GN_MAX_SLABS;
-  gn_stats_kernel<<<dim3(slabs, B), 256, 0, st>>>(x1, C1, x2, C2, HW, slabs, workspace);
+  // enough slabs for >= ~4 CTAs per SM, at least 8 rows per row-lane pass
+  int slabs = (4 * 148 + B - 1) / B;
+  const int R = GN_THREADS / (C / 8);
+  slabs = max(1, min(min(slabs, GN_MAX_SLABS), HW / max(1, 2 * R)));
+  const size_t smem = (size_t)2 * R * C * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    TG_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  TG_CHECK(smem <= 64 * 1024, "groupnorm: smem %zu too large", smem);
+  gn_stats_kernel<<<dim3(slabs, B), GN_THREADS, smem, st>>>(x1, C1, x2, C2, HW, slabs, workspace);
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
-  // ~2 waves of 148 SMs when the tensor is big, never less than 8 rows per CTA
-  int ctas_per_img = max(1, min(HW / 8, (2 * 148 + B - 1) / B));
-  int rows_per_cta = (HW + ctas_per_img - 1) / ctas_per_img;
-  ctas_per_img = (HW + rows_per_cta - 1) / rows_per_cta;
-  gn_apply_kernel<<<dim3(ctas_per_img, B), 256, 0, st>>>(x1, C1, x2, C2, HW, slabs, workspace, gamma, beta, eps, silu,
-                                                         out, rows_per_cta);
+  const int total = HW * (C / 8);
+  gn_apply_kernel<<<dim3((total + 256 * GN_VEC - 1) / (256 * GN_VEC), B), 256, 0, st>>>(
+      x1, C1, x2, C2, HW, slabs, workspace, gamma, beta, eps, silu, out);
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

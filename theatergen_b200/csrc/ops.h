@@ -24,6 +24,9 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
                  __half* out, int ldc, cudaStream_t st);
 
 
+// allocates the per-device split-K workspace (call once outside stream capture; lazily done otherwise)
+int gemm_init();
+
 // GroupNorm(32 groups)(+SiLU) over the channel-concat [x1 | x2] (x2 may be null, C2 = 0); fp32 statistics.
 // workspace: >= B*64*32*2 floats.
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,

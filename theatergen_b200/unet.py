@@ -161,6 +161,18 @@ class TGUNet:
         w["conv_out.w"], w["conv_out.b"] = pack_conv3x3(g("conv_out.weight")), g("conv_out.bias")
         self.w = w
 
+    def load_ip_weights(self, ip_state_dict):
+        """`ip_adapter.{1,3,..,31}.to_{k,v}_ip.weight` in processor order (down, up, mid -- the order of
+        unet.attn_processors the reference loads through a ModuleList, ip_adapter/ip_adapter.py:139-140)."""
+        if not self.has_ip:
+            raise RuntimeError("TGUNet was packed without IP-Adapter rows; construct it with to_k_ip/to_v_ip keys")
+        for n, (p, c, _) in enumerate(_transformer_specs()):
+            idx = 2 * n + 1
+            o = self.transformers[p]["kv_off"]
+            for j, name in enumerate(("to_k_ip", "to_v_ip")):
+                wt = ip_state_dict[f"{idx}.{name}.weight"].to(device=self.device, dtype=torch.float16)
+                self.w["ctxkv.w"][o + (2 + j) * c:o + (3 + j) * c].copy_(wt)
+
     def weight_bytes(self):
         n = sum(v.numel() for v in self.w.values())
         for d in list(self.resnets.values()) + list(self.transformers.values()):
