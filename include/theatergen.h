@@ -59,7 +59,8 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
 
 /* out = [SiLU](GroupNorm32([x1|x2])) for channels-last x1 [B,HW,C1], x2 [B,HW,C2] (x2 NULL when C2 == 0).
  * The up-path torch.cat([hidden, skip], 1) (ip_adapter/unet_2d_blocks.py:2210-2212, 2318-2320) is folded in.
- * workspace: >= B*64*32*2 floats.  Replaces nn.GroupNorm(+SiLU) of diffusers ResnetBlock2D (eps 1e-5),
+ * workspace: >= 16640 + B*4096 floats, ZERO-INITIALISED once (holds self-resetting arrival counters); B <= 256.
+ * Replaces nn.GroupNorm(+SiLU) of diffusers ResnetBlock2D (eps 1e-5),
  * Transformer2DModel.norm (ip_adapter/transformer_2d.py:288, eps 1e-6), conv_norm_out
  * (ip_adapter/unet_2d_condition.py:1117-1119). */
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
@@ -75,6 +76,12 @@ int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half*
  * PerceiverAttention's softmax(QK^T)V (ip_adapter/resampler.py:65-74). */
 int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
                  int ldo, int B, int heads, int Nq, int Nk, int d, float scale, void* stream);
+
+/* Same contract on the tcgen05 path (TMA-fed tiles, S/O accumulators in TMEM) for head dims <= 64: Q/K/V must be
+ * head-padded to 64 columns (head h at column h*64, columns [d,64) zero -- obtained for free by zero rows in the
+ * fused QKV projection weight), Nq == Nk == N with N % 128 == 0.  O is written unpadded ([B*N, heads*d]). */
+int tg_attention_tc(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
+                    int ldo, int B, int heads, int N, int d, float scale, void* stream);
 
 /* IP-Adapter decoupled cross attention (IPAttnProcessor.__call__, ip_adapter/attention_processor.py:478-516):
  *   O = softmax(scale Q Kt^T + add_mask) Vt + ip_scale[b] * softmax(scale Q Ki^T) Vi

@@ -33,6 +33,41 @@ def test_self_attention(B, N, C):
     _close(out, ref, 2e-3, 1e-2, "self-attn")
 
 
+@pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (8, 256, 40), (2, 1024, 48), (1, 128, 8), (2, 512, 32)])
+def test_self_attention_tcgen05(B, N, d):
+    """tcgen05/TMEM flash attention on head-padded (64) Q/K/V vs fp32 SDPA."""
+    from theatergen_b200 import ops
+    heads = 8
+    qkv = torch.zeros((B * N, 3, heads, 64), dtype=torch.float16, device="cuda")
+    qkv[..., :d] = _rand((B * N, 3, heads, d), 1, 1.5)
+    flat = qkv.view(B * N, 3 * heads * 64)
+    P = heads * 64
+    out = ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d)
+    assert out.shape == (B * N, heads * d)
+    q, k, v = [qkv[:, i, :, :d].float().reshape(B, N, heads, d).transpose(1, 2) for i in range(3)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    _close(out, ref, 2e-3, 1e-2, "tcgen05 self-attn")
+    assert torch.equal(out, ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d))
+
+
+def test_self_attention_tcgen05_lazy_rescale():
+    """Scores that keep growing along the key axis force the in-TMEM rescale of O (reference exponent raised by > 2^8
+    several times per row); fully masked-like rows (huge negative scores early) exercise P underflow."""
+    from theatergen_b200 import ops
+    B, N, d, heads = 2, 1024, 40, 8
+    qkv = torch.zeros((B * N, 3, heads, 64), dtype=torch.float16, device="cuda")
+    base = _rand((B * N, 3, heads, d), 7, 1.0)
+    ramp = torch.linspace(0.2, 6.0, N, device="cuda").repeat(B)[:, None, None]     # |k| grows with the key index
+    base[:, 1] = (base[:, 1].float() * ramp).half()
+    qkv[..., :d] = base
+    flat = qkv.view(B * N, 3 * heads * 64)
+    P = heads * 64
+    out = ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d)
+    q, k, v = [qkv[:, i, :, :d].float().reshape(B, N, heads, d).transpose(1, 2) for i in range(3)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+    _close(out, ref, 3e-3, 1e-2, "tcgen05 self-attn (lazy rescale)")
+
+
 def test_self_attention_cross_lengths():
     """Nq != Nk (the resampler: 16 queries over 273 keys) and sharper logits."""
     from theatergen_b200 import ops

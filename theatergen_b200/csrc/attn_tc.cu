@@ -1,0 +1,309 @@
+// tcgen05 flash self-attention for head dims <= 64 (SD-1.5's 64x64 level: N = 4096, d = 40 -- 90 % of the
+// self-attention time).  Q/K/V arrive head-padded to 64 columns (zero weight rows in the fused QKV projection), so
+// every operand tile is the canonical 128-byte-row SWIZZLE_128B layout that TMA writes and tcgen05.mma reads.
+//
+// Per CTA: one (batch, head, 128-query tile); KV tiles of 64 keys stream through a 3-stage TMA ring.
+//   warp 0      TMA producer (Q once, then K_j | V_j per stage)
+//   warp 1      TMEM allocator + single-thread MMA issuer:
+//                   S_j = Q K_j^T           (M=128, N=64, K=ceil(d/16)*16)   -> TMEM S[j&1]
+//                   O_j = P_j V_j           (M=128, N=64, K=64; V is the MN-major B operand) -> TMEM O[j&1]
+//   warps 2..5  one query row per thread (row == TMEM lane): softmax numerators in registers, P_j -> fp16 ->
+//               swizzled smem (the A operand of the second MMA).
+// What bounds this kernel is TMEM->register bandwidth and the MUFU pipe, so the design minimises both:
+//   * O is accumulated IN TMEM across all KV tiles (accumulate flag) and is read exactly once, at the end.
+//     The running max is only a reference exponent: it is raised -- and O rescaled in TMEM (tcgen05.ld / st)
+//     -- only when a row's new maximum exceeds it by more than 2^8 (lazy rescaling; P stays <= 256 in fp16),
+//     which after the first tiles practically never happens.  Per tile only S (128 x 64 fp32) crosses TMEM->RF.
+//   * the softmax denominator is not summed by CUDA cores: column d of each V tile is set to 1.0 in shared
+//     memory, so the tensor core accumulates sum_k P[k] in O[:, d] with exactly the same rescaling as O.
+// S is double-buffered in TMEM so the tensor core computes S_{j+1} while the softmax warps work on S_j; two CTAs
+// fit per SM (96 KB smem, 256 TMEM columns each).  The N x N probabilities never leave the SM
+// (reference: AttnProcessor.__call__, ip_adapter/attention_processor.py:343-356, materialises them in HBM).
+#include "common.cuh"
+#include "ops.h"
+
+namespace tg {
+
+static constexpr int ATQ = 128;   // queries per CTA
+static constexpr int ATK = 64;    // keys per tile
+static constexpr int ATD = 64;    // padded head dim
+static constexpr int AT_STAGES = 3;
+static constexpr int AT_Q_BYTES = ATQ * ATD * 2;        // 16 KB
+static constexpr int AT_KV_BYTES = ATK * ATD * 2;       // 8 KB each
+static constexpr int AT_STAGE_BYTES = 2 * AT_KV_BYTES;  // K | V
+static constexpr int AT_P_OFFSET = AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES;
+static constexpr int AT_P_BYTES = ATQ * ATK * 2;        // 16 KB, double-buffered
+static constexpr int AT_BAR_OFFSET = AT_P_OFFSET + 2 * AT_P_BYTES;
+static constexpr int AT_NUM_BARS = 1 + 2 * AT_STAGES + 2 + 2 + 2 + 2 + 2;  // q, kv full/empty, s f/e, o f/e, p f/e
+static constexpr int AT_SMEM = AT_BAR_OFFSET + AT_NUM_BARS * 8 + 16 + 1024;
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major (N contiguous) SWIZZLE_128B descriptor for the V tile [keys][64]: 8-row K groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;               // LBO: unused (a single 64-element atom along N)
+  d |= (uint64_t)(1024 >> 4) << 32;     // SBO: stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(192, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, __half* __restrict__ O, int ldo, int N, int d,
+               float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + AT_Q_BYTES;
+  uint8_t* sP = smem + AT_P_OFFSET;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAR_OFFSET);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES;
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* o_full = s_empty + 2;
+  uint64_t* o_empty = o_full + 2;
+  uint64_t* p_full = o_empty + 2;  // [2]: P is double-buffered; its reuse is ordered by o_full (P.V of tile j-2 retired)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AT_NUM_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATQ;
+  const int T = N / ATK;
+  const int row_base = b * N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 4);
+      mbar_init(&o_full[s], 1);  // pv_done[s]: P.V of a tile using P buffer s has retired
+    }
+    mbar_init(&p_full[0], 4);
+    mbar_init(&p_full[1], 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;  // S[2] at +0,+64 ; O (single, accumulated) at +128
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, h * ATD, row_base + q0);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+        uint8_t* dst = sKV + s * AT_STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], AT_STAGE_BYTES);
+        tma_load_2d(dst, &tmK, &kv_full[s], h * ATD, row_base + j * ATK);
+        tma_load_2d(dst + AT_KV_BYTES, &tmV, &kv_full[s], h * ATD, row_base + j * ATK);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(ATQ, ATK);                     // A, B K-major
+      // P.V: N = d + 1 (the ones column) rounded up to 16; B (= V) is MN-major
+      const uint32_t idesc_o = make_idesc_f16(ATQ, ((d + 1 + 15) / 16) * 16) | (1u << 16);
+      const int ksteps = (d + 15) / 16;
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      auto issue_s = [&](int j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
+        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sKV + s * AT_STAGE_BYTES);
+        for (int k = 0; k < ksteps; ++k)
+          umma_f16_ss(tS + (j & 1) * 64, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
+                      idesc_s, k > 0 ? 1u : 0u);
+        tc_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const int s = j % AT_STAGES;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_BYTES);
+        const uint32_t pj_addr = p_addr + (j & 1) * AT_P_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATK / 16; ++k)
+          umma_f16_ss(tO, make_smem_desc_sw128(pj_addr + k * 32), make_smem_desc_sw128_mn(v_addr + k * 2048), idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);  // O accumulates in TMEM over all tiles
+        tc_commit(&o_full[j & 1]);
+        tc_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
+    const int tid_s = threadIdx.x - 64;  // 0..127 among the softmax threads
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const int nacc = ((d + 1 + 15) / 16) * 16;  // accumulator columns in use: d outputs + the denominator
+    float m_ref = -INFINITY;  // reference exponent (a stale running max is fine: P <= 2^8)
+    // position of element (key k, column d) inside a swizzled V tile: 16-byte chunk (d/8) ^ (k & 7)
+    const int ones_off = (tid_s & 63) * 128 + ((((d >> 3) ^ (tid_s & 7)) << 4) | ((d & 7) << 1));
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[64];
+      {
+        uint32_t t0[32], t1[32];
+        tmem_ld_32x32b_x32(tS + (j & 1) * 64 + lane_off, t0);
+        tmem_ld_32x32b_x32(tS + (j & 1) * 64 + 32 + lane_off, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sr[i] = t0[i]; sr[32 + i] = t1[i]; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[j & 1]);  // S buffer may be overwritten by tile j+2
+
+      // the ones column of this stage's V tile (its TMA landed before S_j was issued); 64 threads, one store each
+      if (tid_s < 64)
+        *reinterpret_cast<__half*>(sKV + (j % AT_STAGES) * AT_STAGE_BYTES + AT_KV_BYTES + ones_off) = __float2half(1.f);
+
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      if (j == 0) {
+        m_ref = mx;  // O is still empty (the first P.V overwrites it)
+      } else {
+        const bool need = (mx - m_ref) * scale_log2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          // lazy rescale of this warp's 32 O rows in TMEM: only legal while no P.V is in flight -> P.V_{j-1} retired
+          mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float f = need ? exp2f((m_ref - mx) * scale_log2) : 1.f;
+          if (need) m_ref = mx;
+          for (int c = 0; c < nacc; c += 32) {
+            uint32_t t[32];
+            tmem_ld_32x32b_x32(tO + c + lane_off, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * f);
+            tmem_st_32x32b_x32(tO + c + lane_off, t);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+      }
+      const float msc = m_ref * scale_log2;
+
+      // P buffer j&1 was last read by P.V of tile j-2
+      mbar_wait(&o_full[j & 1], ((j >> 1) & 1) ^ 1);
+      uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // 8 keys -> one 16-byte chunk of the swizzled P row
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float x0 = __uint_as_float(sr[8 * i + 2 * k]) * scale_log2 - msc;
+          const float x1 = __uint_as_float(sr[8 * i + 2 * k + 1]) * scale_log2 - msc;
+          // fp32 exp2 (one MUFU each -- ex2.f16x2 is split into two MUFU ops on sm_100 anyway, and with a stale
+          // reference exponent the dominant terms sit at |x| up to 8 where an fp16 argument would cost 0.3 %)
+          float p0, p1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+          const __half2 hp = __floats2half2_rn(p0, p1);
+          pk[k] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        *reinterpret_cast<uint4*>(p_row + ((i ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+    // epilogue: O (and the denominator in column d) is read from TMEM exactly once
+    mbar_wait(&o_full[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    float acc[ATD];
+    {
+      uint32_t t0[32], t1[32];
+      tmem_ld_32x32b_x32(tO + lane_off, t0);
+      if (nacc > 32) tmem_ld_32x32b_x32(tO + 32 + lane_off, t1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = __uint_as_float(t0[i]);
+        acc[32 + i] = nacc > 32 ? __uint_as_float(t1[i]) : 0.f;
+      }
+    }
+    float l_run = 0.f;
+#pragma unroll
+    for (int i = 0; i < ATD; ++i)
+      if (i == d) l_run = acc[i];
+    const float inv = 1.f / l_run;
+    __half* orow = O + (size_t)(row_base + q0 + r) * ldo + h * d;
+    const int nvec = d / 8;  // d is a multiple of 8
+#pragma unroll
+    for (int i = 0; i < ATD / 8; ++i) {
+      if (i < nvec) {
+        uint4 o;
+        __half2* hh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hh[k] = __floats2half2_rn(acc[8 * i + 2 * k] * inv, acc[8 * i + 2 * k + 1] * inv);
+        *reinterpret_cast<uint4*>(orow + 8 * i) = o;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
+                 int B, int heads, int N, int d, float scale, cudaStream_t st) {
+  TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d + 1 <= ATD, "attention_tc: N=%d (multiple of 128) d=%d (<=56, multiple of 8)", N, d);
+  TG_CHECK(ldo % 8 == 0 && (d * 2) % 16 == 0, "attention_tc: output pitch/head offset must be 16B aligned");
+  static bool attr = false;
+  if (!attr) {
+    TG_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr = true;
+  }
+  CUtensorMap tq, tk, tv;
+  const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * ATD;
+  if (make_tmap_2d(&tq, Q, rows, cols, ldq, ATQ)) return -1;
+  if (make_tmap_2d(&tk, K, rows, cols, ldk, ATK)) return -1;
+  if (make_tmap_2d(&tv, V, rows, cols, ldv, ATK)) return -1;
+  attn_tc_kernel<<<dim3(N / ATQ, heads, B), 192, AT_SMEM, st>>>(tq, tk, tv, O, ldo, N, d,
+                                                               scale * 1.4426950408889634f);
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tg

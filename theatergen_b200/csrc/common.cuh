@@ -210,6 +210,19 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below fp16 resolution): 2 MUFU + ~12 FMA
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p, e, 1.f);
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

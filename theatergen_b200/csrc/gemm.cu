@@ -357,9 +357,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             for (int i = 0; i < 32; ++i) v[h2 * 32 + i] = __uint_as_float(r[i]);
           }
         } else {
-          // GEGLU: accumulator columns packed per 64 as [32 value | 32 gate]; bias packed the same way.  The
-          // reference rounds both halves of the projection to fp16 before the gated product
-          // (ip_adapter/attention.py:359-367): keep that rounding so GELU sees the same gate.
+          // GEGLU: accumulator columns packed per 64 as [32 value | 32 gate]; bias packed the same way
+          // (ip_adapter/attention.py:359-367).  value * gelu_erf(gate) is formed in fp32 and rounded once.
 #pragma unroll
           for (int hlf = 0; hlf < EC / 32; ++hlf) {
             uint32_t ra[32], rg[32];
@@ -377,12 +376,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               for (int jj = 0; jj < 4; ++jj) {
                 const float2 fa = __half22float2(ha[jj]), fg = __half22float2(hg[jj]);
                 const int ee = i * 8 + jj * 2;
-                const float a0 = __half2float(__float2half_rn(__uint_as_float(ra[ee]) + fa.x));
-                const float a1 = __half2float(__float2half_rn(__uint_as_float(ra[ee + 1]) + fa.y));
-                const float g0 = __half2float(__float2half_rn(__uint_as_float(rg[ee]) + fg.x));
-                const float g1 = __half2float(__float2half_rn(__uint_as_float(rg[ee + 1]) + fg.y));
-                v[hlf * 32 + ee] = a0 * gelu_erf_f(g0);
-                v[hlf * 32 + ee + 1] = a1 * gelu_erf_f(g1);
+                const float a0 = __uint_as_float(ra[ee]) + fa.x, a1 = __uint_as_float(ra[ee + 1]) + fa.y;
+                const float g0 = __uint_as_float(rg[ee]) + fg.x, g1 = __uint_as_float(rg[ee + 1]) + fg.y;
+                v[hlf * 32 + ee] = a0 * gelu_erf_fast(g0);
+                v[hlf * 32 + ee + 1] = a1 * gelu_erf_fast(g1);
               }
             }
           }

@@ -17,6 +17,7 @@ static constexpr int GN_GROUPS = 32;
 static constexpr int GN_MAX_SLABS = 64;
 static constexpr int GN_THREADS = 320;  // >= C/8 for C <= 2560
 static constexpr int GN_VEC = 4;
+static constexpr int GN_MAX_BATCH = 256;
 
 // partial[b][slab][g][2] = (sum, sumsq) over the slab's pixels of group g.
 // Thread (r, chunk) owns one 16-byte column chunk (8 channels) and walks rows r, r+R, ... of the slab with four
@@ -24,7 +25,7 @@ static constexpr int GN_VEC = 4;
 // thread per group adds its channels in a fixed order: no atomics -> bit-reproducible statistics.
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
-                float* __restrict__ partial) {
+                float* __restrict__ partial, float* __restrict__ stats, int* __restrict__ counters, float eps) {
   const int b = blockIdx.y, slab = blockIdx.x;
   const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
   const int rows_per = (HW + slabs - 1) / slabs;
@@ -84,71 +85,91 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     o[0] = s;
     o[1] = q;
   }
-}
-
-// normalise (+SiLU): every thread handles GN_VEC 16-byte vectors, all loads issued before any math
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
-                const float* __restrict__ partial, const __half* __restrict__ gamma,
-                const __half* __restrict__ beta, float eps, int silu, __half* __restrict__ out) {
-  const int b = blockIdx.y;
-  const int C = C1 + C2, cpg = C / GN_GROUPS;
-  __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+  // the last slab-CTA of this image to arrive folds the partials (fixed order) into mean / rstd
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(counters + b, 1);
+    s_last = old == slabs - 1;
+    if (s_last) counters[b] = 0;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (threadIdx.x < GN_GROUPS) {
     float s = 0.f, q = 0.f;
     const float* p = partial + ((size_t)b * slabs * GN_GROUPS + threadIdx.x) * 2;
-    for (int i = 0; i < slabs; ++i, p += GN_GROUPS * 2) { s += p[0]; q += p[1]; }
+    for (int i = 0; i < slabs; ++i, p += GN_GROUPS * 2) { s += __ldcg(p); q += __ldcg(p + 1); }
     const float n = (float)HW * cpg;
     const float mean = s / n;
     const float var = fmaxf(q / n - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+    stats[((size_t)b * GN_GROUPS + threadIdx.x) * 2] = mean;
+    stats[((size_t)b * GN_GROUPS + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
   }
-  __syncthreads();
-  const int c8n = C / 8;
-  const int total = HW * c8n;
-  const int base = blockIdx.x * (256 * GN_VEC) + threadIdx.x;
-  uint4 v[GN_VEC];
-  int cc[GN_VEC], rr[GN_VEC];
-#pragma unroll
-  for (int u = 0; u < GN_VEC; ++u) {
-    const int i = base + u * 256;
-    if (i < total) {
-      rr[u] = i / c8n;
-      cc[u] = (i - rr[u] * c8n) * 8;
-      const __half* src = (cc[u] < C1) ? x1 + ((size_t)b * HW + rr[u]) * C1 + cc[u]
-                                       : x2 + ((size_t)b * HW + rr[u]) * C2 + (cc[u] - C1);
-      v[u] = *reinterpret_cast<const uint4*>(src);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < GN_VEC; ++u) {
-    const int i = base + u * 256;
-    if (i >= total) continue;
-    const int c = cc[u];
+}
+
+// normalise (+SiLU): thread (r, chunk) owns one 16-byte column chunk; its 8 scale/shift pairs
+// (a = rstd*gamma, s = beta - mean*a) live in registers, rows are streamed with four 16-byte loads in flight.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
+                const float* __restrict__ stats, const __half* __restrict__ gamma,
+                const __half* __restrict__ beta, int silu, __half* __restrict__ out) {
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
+  const int R = GN_THREADS / c8n;
+  const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  if (rl >= R) return;
+  const int c = chunk * 8;
+  float sa[8], sb[8];
+  {
     const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + c));
     const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + c));
-    const __half* hv = reinterpret_cast<const __half*>(&v[u]);
     const __half* hg = reinterpret_cast<const __half*>(&gm);
     const __half* hb = reinterpret_cast<const __half*>(&bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c + j) / cpg;
+      const float mean = stats[((size_t)b * GN_GROUPS + g) * 2], rstd = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
+      sa[j] = rstd * __half2float(hg[j]);
+      sb[j] = __half2float(hb[j]) - mean * sa[j];
+    }
+  }
+  const __half* src;
+  int ld;
+  if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
+  src += (size_t)b * HW * ld;
+  __half* dst = out + (size_t)b * HW * C + c;
+  const int rows_per = (HW + slabs - 1) / slabs;
+  const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
+  auto emit = [&](const uint4& v, int r) {
+    const __half* hv = reinterpret_cast<const __half*>(&v);
     uint4 o;
     __half* ho = reinterpret_cast<__half*>(&o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      float y = (__half2float(hv[j]) - s_mean[g]) * s_rstd[g] * __half2float(hg[j]) + __half2float(hb[j]);
+      float y = fmaf(__half2float(hv[j]), sa[j], sb[j]);
       if (silu) y = silu_f(y);
       ho[j] = __float2half_rn(y);
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)b * HW + rr[u]) * C + c) = o;
+    *reinterpret_cast<uint4*>(dst + (size_t)r * C) = o;
+  };
+  int r = r0 + rl;
+  for (; r + 3 * R < r1; r += 4 * R) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(v[u], r + u * R);
   }
+  for (; r < r1; r += R) emit(*reinterpret_cast<const uint4*>(src + (size_t)r * ld), r);
 }
 
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st) {
   const int C = C1 + C2;
   TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN_THREADS, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
-  TG_CHECK(workspace != nullptr, "groupnorm: workspace (B*64*32*2 floats) required");
+  TG_CHECK(workspace != nullptr, "groupnorm: zero-initialised workspace (16640 + B*4096 floats) required");
   // enough slabs for >= ~4 CTAs per SM, at least 8 rows per row-lane pass
   int slabs = (4 * 148 + B - 1) / B;
   const int R = GN_THREADS / (C / 8);
@@ -160,12 +181,17 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
     attr = true;
   }
   TG_CHECK(smem <= 64 * 1024, "groupnorm: smem %zu too large", smem);
-  gn_stats_kernel<<<dim3(slabs, B), GN_THREADS, smem, st>>>(x1, C1, x2, C2, HW, slabs, workspace);
+  // workspace layout (fixed offsets, independent of B): [256 arrival counters][256 x 32 x (mean, rstd)][partials]
+  TG_CHECK(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
+  int* counters = reinterpret_cast<int*>(workspace);
+  float* stats = workspace + GN_MAX_BATCH;
+  float* partial = stats + (size_t)GN_MAX_BATCH * GN_GROUPS * 2;
+  gn_stats_kernel<<<dim3(slabs, B), GN_THREADS, smem, st>>>(x1, C1, x2, C2, HW, slabs, partial, stats, counters, eps);
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
-  const int total = HW * (C / 8);
-  gn_apply_kernel<<<dim3((total + 256 * GN_VEC - 1) / (256 * GN_VEC), B), 256, 0, st>>>(
-      x1, C1, x2, C2, HW, slabs, workspace, gamma, beta, eps, silu, out);
+  int aslabs = (8 * 148 + B - 1) / B;  // ~8 CTAs per SM in flight, >= 4 rows per row-lane
+  aslabs = max(1, min(aslabs, HW / max(1, 4 * R)));
+  gn_apply_kernel<<<dim3(aslabs, B), GN_THREADS, 0, st>>>(x1, C1, x2, C2, HW, aslabs, stats, gamma, beta, silu, out);
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

@@ -37,6 +37,9 @@ int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* 
 // O[b, n, h*d..] = softmax(scale * Q K^T) V per (b, h); row pitches in elements
 int attention_flash(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
                     int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t st);
+// tcgen05 flash self-attention; Q/K/V head-padded to 64 columns (head h at column h*64), N % 128 == 0, d <= 64
+int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
+                 int B, int heads, int N, int d, float scale, cudaStream_t st);
 // text + image-token cross attention (see attn.cu)
 int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
                        const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,

@@ -118,8 +118,9 @@ _GN_WS = {}
 def _gn_workspace(device, B):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _GN_WS.get(key)
-    if ws is None or ws.numel() < B * 64 * 32 * 2:
-        ws = torch.empty(max(B, 16) * 64 * 32 * 2, dtype=torch.float32, device=device)
+    if ws is None or ws.numel() < 16640 + B * 4096:
+        # [256 arrival counters (start at zero, self-resetting)][256x32x2 mean/rstd][partials B x 64 x 32 x 2]
+        ws = torch.zeros(16640 + max(B, 32) * 4096, dtype=torch.float32, device=device)
         _GN_WS[key] = ws
     return ws
 
@@ -165,6 +166,21 @@ def attention(q, k, v, B, heads, scale=None, out=None):
                 lambda: _lib.lib().tg_attention(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out),
                                                 out.stride(0), B, heads, Nq, Nk, d, float(scale), _stream()))
     _lib.check(rc, "tg_attention")
+    return out
+
+
+def attention_tc(q, k, v, B, heads, d, scale=None, out=None):
+    """tcgen05 flash attention: q/k/v are [B*N, heads*64] views (head-padded to 64, pad columns zero)."""
+    _chk16(q, k, v, out)
+    N = q.shape[0] // B
+    if scale is None:
+        scale = d ** -0.5
+    if out is None:
+        out = torch.empty((B * N, heads * d), dtype=torch.float16, device=q.device)
+    rc = _timed("attn_tc_kernel", 4.0 * B * heads * N * N * d, 2.0 * B * heads * d * 4 * N,
+                lambda: _lib.lib().tg_attention_tc(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out),
+                                                   out.stride(0), B, heads, N, d, float(scale), _stream()))
+    _lib.check(rc, "tg_attention_tc")
     return out
 
 

@@ -136,7 +136,16 @@ class TGUNet:
             t["pow"], t["pob"] = g(p + ".proj_out.weight").reshape(c, c).contiguous(), g(p + ".proj_out.bias")
             for n in ("norm1", "norm2", "norm3"):
                 t[n + "g"], t[n + "b"] = g(f"{tb_}.{n}.weight"), g(f"{tb_}.{n}.bias")
-            t["qkvw"] = torch.cat([g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"], 0).contiguous()
+            qkv = [g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"]
+            t["qkv_pad"] = (c // HEADS) < 64  # d = 40: pad every head to 64 rows (zero weights) for the tcgen05 path
+            if t["qkv_pad"]:
+                d_ = c // HEADS
+                padded = torch.zeros((3, HEADS, 64, c), dtype=torch.float16, device=dev)
+                for i_, m_ in enumerate(qkv):
+                    padded[i_, :, :d_] = m_.view(HEADS, d_, c)
+                t["qkvw"] = padded.view(3 * HEADS * 64, c).contiguous()
+            else:
+                t["qkvw"] = torch.cat(qkv, 0).contiguous()
             t["o1w"], t["o1b"] = g(f"{tb_}.attn1.to_out.0.weight"), g(f"{tb_}.attn1.to_out.0.bias")
             t["q2w"] = g(f"{tb_}.attn2.to_q.weight")
             t["o2w"], t["o2b"] = g(f"{tb_}.attn2.to_out.0.weight"), g(f"{tb_}.attn2.to_out.0.bias")
@@ -205,7 +214,13 @@ class TGUNet:
         # self attention
         ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
         qkv = ops.gemm(ln, t["qkvw"])
-        a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
+        if t["qkv_pad"] and (H * W) % 128 == 0:
+            P = HEADS * 64
+            a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], B, HEADS, C // HEADS)
+        elif t["qkv_pad"]:
+            raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
+        else:
+            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
         h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
         # cross attention (+ image tokens)
         ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
