@@ -30,8 +30,7 @@ def test_processors_match_reference_outputs(case):
     proc = IPAttnProcessor(C, 768, scale=0.4, num_tokens=4)
     attn2.set_processor(proc)
     attn1.load_state_dict({k[6:]: v for k, v in sd.items() if k.startswith("attn1.")})
-    attn2.load_state_dict({k[6:]: v for k, v in sd.items() if k.startswith("attn2.") and ".processor." not in k})
-    proc.load_state_dict({k[len("attn2.processor."):]: v for k, v in sd.items() if ".processor." in k})
+    attn2.load_state_dict({k[6:]: v for k, v in sd.items() if k.startswith("attn2.")})  # incl. processor.to_{k,v}_ip
     for m in (attn1, attn2, proc):
         m.half().cuda()
     x = torch.randn(2, N, C, generator=gen(g["seeds"]["x"])).half().cuda()

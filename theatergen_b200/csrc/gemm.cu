@@ -14,12 +14,19 @@
 // single-thread tcgen05.mma issuer, warps2..5 = epilogue.  The accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of item i (TMEM -> registers -> bias/temb/activation/residual -> swizzled
 // smem -> TMA store) overlaps the main loop of item i+1.
+// TMA multicast (MC = true, used whenever there are >= 2 M-tiles): CTAs run as clusters of two that own vertically
+// adjacent 128-row tiles of the same N-tile; each CTA fetches half of the B (weight) tile and multicasts it into
+// both CTAs' shared memory, so the L2->SM traffic per CTA and k-block drops from 16 KB + 128*BN to 16 KB + 64*BN
+// (the smem->tensor feed, not the tensor pipe, is what bounds these tiles).  Every CTA still issues its own
+// 128 x BN tcgen05.mma; a stage is released to BOTH producers by a multicast tcgen05.commit.
 // Split-K (small-M, long-K layers: the 8x8 / 16x16 levels stream 30-60 MB of weights through <= 40 tiles):
 // every split writes its fp32 partial tile to an L2-resident workspace, a per-tile semaphore elects the last
 // arriving CTA, which sums the partials in a FIXED order (bit-reproducible) and runs the fused epilogue.
 // Replaces, for the hot path, every cuBLAS/cuDNN call the reference issues through
 // nn.Linear / nn.Conv2d (reference: ip_adapter/attention_processor.py:333-359,461-520,
 // ip_adapter/attention.py:269-367, ip_adapter/transformer_2d.py:288-342, diffusers ResnetBlock2D).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -28,7 +35,7 @@ namespace tg {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, alternating column chunks
-static constexpr int EPI_BUF_BYTES = 32 * 128;   // 32 rows x 64 fp16 per warp per buffer
+static constexpr int EPI_BUF_BYTES = 2 * 32 * 64;  // per warp: two staging buffers of 32 rows x 32 fp16
 static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
 static constexpr int MAX_SPLIT = 8;
 static constexpr size_t SPLITK_WS_BYTES = (size_t)64 << 20;
@@ -67,6 +74,29 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -88,56 +118,54 @@ __device__ __forceinline__ void add_h8(float* v, uint4 b) {
   }
 }
 
-// EC (64 or 32) output columns of one row: bias / temb / activation / residual, then fp16 into the swizzled staging
-// buffer (row pitch EC*2 bytes; SWIZZLE_128B for EC = 64, SWIZZLE_64B for EC = 32 -- must match the C tensor map).
-template <int EC>
-__device__ __forceinline__ void epilogue_row(const GemmArgs& g, float (&v)[EC], const uint4 (&res)[EC / 8], int m, int n,
+// 32 output columns of one row: bias / temb / activation / residual, then fp16 into the swizzled staging buffer
+// (32 rows x 64 bytes per warp, SWIZZLE_64B: 16-byte chunk i of row r lives at chunk i ^ ((r >> 1) & 3) -- must match
+// the C tensor map).
+__device__ __forceinline__ void epilogue_row(const GemmArgs& g, float (&v)[32], const uint4 (&res)[4], int m, int n,
                                              bool row_ok, uint8_t* stage_row, int row_in_warp) {
   if (g.bias && g.act != 2) {
     const uint4* bp = reinterpret_cast<const uint4*>(g.bias + n);
 #pragma unroll
-    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], __ldg(bp + i));
+    for (int i = 0; i < 4; ++i) add_h8(&v[i * 8], __ldg(bp + i));
   }
   if (row_ok && g.rowbias) {
     const uint4* bp = reinterpret_cast<const uint4*>(g.rowbias + (size_t)(m / g.rows_per_image) * g.rowbias_ld + n);
 #pragma unroll
-    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], __ldg(bp + i));
+    for (int i = 0; i < 4; ++i) add_h8(&v[i * 8], __ldg(bp + i));
   }
   if (g.act == 1) {
 #pragma unroll
-    for (int i = 0; i < EC; ++i) v[i] = silu_f(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
   } else if (g.act == 3) {
 #pragma unroll
-    for (int i = 0; i < EC; ++i) v[i] = gelu_erf_f(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
   }
   if (row_ok && g.residual) {
 #pragma unroll
-    for (int i = 0; i < EC / 8; ++i) add_h8(&v[i * 8], res[i]);
+    for (int i = 0; i < 4; ++i) add_h8(&v[i * 8], res[i]);
   }
 #pragma unroll
-  for (int i = 0; i < EC / 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
     uint4 o;
     __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       h[j] = __floats2half2_rn(v[i * 8 + j * 2] * g.out_scale, v[i * 8 + j * 2 + 1] * g.out_scale);
-    // 16-byte chunk i of row r lives at chunk (i ^ (r & 7)) [128B swizzle] / (i ^ ((r >> 1) & 3)) [64B swizzle]
-    const int sw = EC == 64 ? (i ^ (row_in_warp & 7)) : (i ^ ((row_in_warp >> 1) & 3));
-    *reinterpret_cast<uint4*>(stage_row + (sw << 4)) = o;
+    *reinterpret_cast<uint4*>(stage_row + ((i ^ ((row_in_warp >> 1) & 3)) << 4)) = o;
   }
 }
 
-// residual prefetch: issued before the accumulator wait so the global latency overlaps it
-template <int EC>
-__device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[EC / 8], int m, int n, bool row_ok) {
+// residual prefetch (global, row-contiguous 64 bytes per thread): issued one chunk ahead so its latency overlaps the
+// accumulator wait / the previous chunk's math
+__device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[4], int m, int n, bool row_ok) {
   if (row_ok && g.residual) {
     const uint4* rp = reinterpret_cast<const uint4*>(g.residual + (size_t)m * g.ldr + n);
 #pragma unroll
-    for (int i = 0; i < EC / 8; ++i) res[i] = __ldg(rp + i);
+    for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
@@ -155,7 +183,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int nk = g.K / BK;
   const int S = g.splits;
-  const int num_work = g.num_m * g.num_n * S;
+  // MC: a cluster of two CTAs owns the M-tile pair (2*pm, 2*pm + 1); rank selects the tile and the B half it fetches
+  const int rank = MC ? (int)cluster_ctarank() : 0;
+  const int worker = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int rows_m = MC ? (g.num_m + 1) / 2 : g.num_m;  // M-tile rows of the work grid
+  const int num_work = rows_m * g.num_n * S;
   constexpr uint32_t ACC_STRIDE = BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
 
@@ -165,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: both CTAs' MMAs must have drained the slot
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -179,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -188,9 +222,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int it = 0;  // k-iteration counter across work items (ring position)
       const int hw = g.H * g.W;
       const int cblk = g.mode == 1 ? g.Cin / BK : 1;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-        const int tile = w / S, split = w - tile * S;
-        const int m0 = (tile / g.num_n) * BM, n0 = (tile % g.num_n) * BN;
+      for (int w = worker; w < num_work; w += num_workers) {
+        const int wt = w / S, split = w - wt * S;
+        const int m0 = ((wt / g.num_n) * (MC ? 2 : 1) + rank) * BM, n0 = (wt % g.num_n) * BN;
         const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
         int conv_b0 = 0, conv_y0 = 0;
         if (g.mode == 1) {
@@ -216,7 +250,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int ky = tap / 3, kx = tap - ky * 3;
             tma_load_4d(sa, &tmA1, &full_bar[s], c0, kx - 1, conv_y0 + ky - 1, conv_b0);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          if (MC)  // my half of the weight tile, delivered to both CTAs of the pair
+            tma_load_2d_mc(sb + rank * (L::B_BYTES / 2), &tmB, &full_bar[s], kb * BK, n0 + rank * (BN / 2), 0x3);
+          else
+            tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
         }
       }
     }
@@ -225,8 +262,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BM, BN);
       int it = 0, j = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++j) {
-        const int tile = w / S, split = w - tile * S;
+      for (int w = worker; w < num_work; w += num_workers, ++j) {
+        const int wt = w / S, split = w - wt * S;
         const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
         const int as = j & 1;
         mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue drained this accumulator
@@ -245,24 +282,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
             umma_f16_ss(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          if (MC)
+            tc_commit_mc(&empty_bar[s], 0x3);  // the slot is written by both producers: release it to both
+          else
+            tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
         tc_commit(&acc_full[as]);  // accumulator complete
       }
     }
   } else {
     // ===== epilogue warps =====
-    // warp (2 + e): TMEM lane quarter q = warp & 3 (hardware rule), column-chunk parity half = e >> 2
-    constexpr int EC = (BN % 64 == 0) ? 64 : 32;
+    // warp (2 + e): TMEM lane quarter q = warp & 3 (hardware rule), column-chunk parity half = e >> 2.
+    // Work unit: 32 output columns (64 accumulator columns for GEGLU) of 32 rows -> one 2 KB TMA store; two staging
+    // buffers per warp so the store of chunk i overlaps the math of chunk i+1.
+    constexpr int EC = 32;
     const int e = warp - 2;
     const int q = warp & 3;
     const int half = e >> 2;
     const int row_in_tile = q * 32 + lane;
-    uint8_t* my_stage = smem + L::EPI_OFFSET + e * EPI_BUF_BYTES;  // one staging buffer per epilogue warp
+    uint8_t* my_stage = smem + L::EPI_OFFSET + e * EPI_BUF_BYTES;  // 2 x 2 KB
     int j = 0, chunk_ctr = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++j) {
-      const int tile = w / S, split = w - tile * S;
-      const int m0 = (tile / g.num_n) * BM, n0 = (tile % g.num_n) * BN;
+    for (int w = worker; w < num_work; w += num_workers, ++j) {
+      const int wt = w / S, split = w - wt * S;
+      const int m_blk = (wt / g.num_n) * (MC ? 2 : 1) + rank, n_blk = wt % g.num_n;
+      const int tile = m_blk * g.num_n + n_blk;  // output-tile index (split-K workspace / semaphore slot)
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int as = j & 1;
       const int m = m0 + row_in_tile;
       const bool row_ok = m < g.M;
@@ -272,6 +316,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         // ---- split-K: spill the fp32 partial tile, elect the last arriving CTA of this tile ----
         mbar_wait(&acc_full[as], (j >> 1) & 1);
         tc_fence_after();
+        if (m0 >= g.M) {  // padding tile of an odd M-tile pair: nothing to reduce, just recycle the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          continue;
+        }
         float4* wsp = reinterpret_cast<float4*>(g.ws) + ((size_t)(tile * S + split) * (BN / 4)) * BM + row_in_tile;
 #pragma unroll 1
         for (int c = half * 32; c < BN; c += 64) {
@@ -303,11 +353,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const float4* rsp = reinterpret_cast<const float4*>(g.ws) + ((size_t)tile * S * (BN / 4)) * BM + row_in_tile;
 #pragma unroll 1
         for (int c = half * EC; c < BN; c += 2 * EC, ++chunk_ctr) {
-          uint8_t* buf = my_stage;
-          uint4 res[EC / 8];
-          load_residual<EC>(g, res, m, n0 + c, row_ok);
-          if (lane == 0) bulk_wait_read<0>();
-          __syncwarp();
+          uint8_t* buf = my_stage + (chunk_ctr & 1) * (EPI_BUF_BYTES / 2);
+          uint4 res[4];
+          load_residual(g, res, m, n0 + c, row_ok);
           float v[EC];
 #pragma unroll
           for (int i = 0; i < EC; ++i) v[i] = 0.f;
@@ -319,7 +367,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
             }
           }
-          epilogue_row<EC>(g, v, res, m, n0 + c, row_ok, buf + lane * (EC * 2), lane);
+          if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+          __syncwarp();
+          epilogue_row(g, v, res, m, n0 + c, row_ok, buf + lane * 64, lane);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -331,70 +381,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
 
       const int step = g.act == 2 ? 2 * EC : EC;  // accumulator columns consumed per EC output columns
-      bool waited = false;
+      const int c_first = half * step;
+      uint4 res_next[4];
+      if (c_first < BN) load_residual(g, res_next, m, g.act == 2 ? (n0 + c_first) >> 1 : n0 + c_first, row_ok);
+      mbar_wait(&acc_full[as], (j >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = half * step; c < BN; c += 2 * step, ++chunk_ctr) {
-        uint8_t* buf = my_stage;
+      for (int c = c_first; c < BN; c += 2 * step, ++chunk_ctr) {
+        uint8_t* buf = my_stage + (chunk_ctr & 1) * (EPI_BUF_BYTES / 2);
         const int n_out = g.act == 2 ? (n0 + c) >> 1 : n0 + c;
-        uint4 res[EC / 8];
-        load_residual<EC>(g, res, m, n_out, row_ok);
-        if (!waited) {
-          mbar_wait(&acc_full[as], (j >> 1) & 1);
-          tc_fence_after();
-          waited = true;
-        }
-        // the TMA store that last read this warp's staging buffer must have finished reading it
-        if (lane == 0) bulk_wait_read<0>();
-        __syncwarp();
+        uint4 res[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) res[i] = res_next[i];
+        const int c_nxt = c + 2 * step;
+        if (c_nxt < BN) load_residual(g, res_next, m, g.act == 2 ? (n0 + c_nxt) >> 1 : n0 + c_nxt, row_ok);
         float v[EC];
         if (g.act != 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(lane_addr + c, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h2 = 0; h2 < EC / 32; ++h2) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(lane_addr + c + h2 * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[h2 * 32 + i] = __uint_as_float(r[i]);
-          }
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         } else {
           // GEGLU: accumulator columns packed per 64 as [32 value | 32 gate]; bias packed the same way
           // (ip_adapter/attention.py:359-367).  value * gelu_erf(gate) is formed in fp32 and rounded once.
+          uint32_t ra[32], rg[32];
+          tmem_ld_32x32b_x32(lane_addr + c, ra);
+          tmem_ld_32x32b_x32(lane_addr + c + 32, rg);
+          tmem_ld_wait();
+          const uint4* bpa = reinterpret_cast<const uint4*>(g.bias + n0 + c);
+          const uint4* bpg = bpa + 4;
 #pragma unroll
-          for (int hlf = 0; hlf < EC / 32; ++hlf) {
-            uint32_t ra[32], rg[32];
-            tmem_ld_32x32b_x32(lane_addr + c + hlf * 64, ra);
-            tmem_ld_32x32b_x32(lane_addr + c + hlf * 64 + 32, rg);
-            tmem_ld_wait();
-            const uint4* bpa = reinterpret_cast<const uint4*>(g.bias + n0 + c + hlf * 64);
-            const uint4* bpg = bpa + 4;
+          for (int i = 0; i < 4; ++i) {
+            const uint4 ba = __ldg(bpa + i), bg = __ldg(bpg + i);
+            const __half2* ha = reinterpret_cast<const __half2*>(&ba);
+            const __half2* hg = reinterpret_cast<const __half2*>(&bg);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 ba = __ldg(bpa + i), bg = __ldg(bpg + i);
-              const __half2* ha = reinterpret_cast<const __half2*>(&ba);
-              const __half2* hg = reinterpret_cast<const __half2*>(&bg);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float2 fa = __half22float2(ha[jj]), fg = __half22float2(hg[jj]);
-                const int ee = i * 8 + jj * 2;
-                const float a0 = __uint_as_float(ra[ee]) + fa.x, a1 = __uint_as_float(ra[ee + 1]) + fa.y;
-                const float g0 = __uint_as_float(rg[ee]) + fg.x, g1 = __uint_as_float(rg[ee + 1]) + fg.y;
-                v[hlf * 32 + ee] = a0 * gelu_erf_fast(g0);
-                v[hlf * 32 + ee + 1] = a1 * gelu_erf_fast(g1);
-              }
+            for (int jj = 0; jj < 4; ++jj) {
+              const float2 fa = __half22float2(ha[jj]), fg = __half22float2(hg[jj]);
+              const int ee = i * 8 + jj * 2;
+              const float a0 = __uint_as_float(ra[ee]) + fa.x, a1 = __uint_as_float(ra[ee + 1]) + fa.y;
+              const float g0 = __uint_as_float(rg[ee]) + fg.x, g1 = __uint_as_float(rg[ee + 1]) + fg.y;
+              v[ee] = a0 * gelu_erf_fast(g0);
+              v[ee + 1] = a1 * gelu_erf_fast(g1);
             }
           }
         }
-        epilogue_row<EC>(g, v, res, m, n_out, row_ok, buf + lane * (EC * 2), lane);
+        if (lane == 0) bulk_wait_read<1>();  // the store issued two chunks ago has finished reading this buffer
+        __syncwarp();
+        epilogue_row(g, v, res, m, n_out, row_ok, buf + lane * 64, lane);
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&tmC, buf, n_out, m0 + q * 32);  // rows >= M are clipped by the tensor map
           bulk_commit();
         }
-      }
-      if (!waited) {  // this warp had no chunk in this tile (narrow tile): still has to observe the phase
-        mbar_wait(&acc_full[as], (j >> 1) & 1);
-        tc_fence_after();
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -405,6 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tc_fence_before();
   }
   __syncthreads();
+  if (MC) cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -443,23 +485,51 @@ int gemm_init() {
   return get_scratch(&s);
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
-                       GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
+template <int BN, int STAGES, bool MC>
+static int launch_gemm_impl(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
+                            GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, MC>;
   if (!attr_set) {
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   CUtensorMap b;
-  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, BN)) return -1;
-  const int work = g.num_m * g.num_n * g.splits;
-  kern<<<work < sc.num_sms ? work : sc.num_sms, NUM_THREADS, L::TOTAL, st>>>(a1, a2, b, c, g);
+  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, MC ? BN / 2 : BN)) return -1;
+  const int rows_m = MC ? (g.num_m + 1) / 2 : g.num_m;
+  const int work = rows_m * g.num_n * g.splits;
+  const int max_workers = MC ? sc.num_sms / 2 : sc.num_sms;
+  const int workers = work < max_workers ? work : max_workers;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(MC ? 2 * workers : workers);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TG_CUDA(cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, g));
   TG_COUNT_LAUNCH();
-  TG_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
+                       GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
+  // Multicast pairs (two M-tiles sharing a weight tile) are opt-in (TG_GEMM_MC=1): measured on B200 they do not
+  // help -- these tiles are bound by per-SM smem ingest (~50 B/clk), which multicast does not reduce.
+  static int use_mc = -1;
+  if (use_mc < 0) {
+    const char* e = getenv("TG_GEMM_MC");
+    use_mc = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_mc && g.num_m >= 2) return launch_gemm_impl<BN, STAGES, true>(a1, a2, Wt, c, g, sc, st);
+  return launch_gemm_impl<BN, STAGES, false>(a1, a2, Wt, c, g, sc, st);
 }
 
 // Tile width / split choice: minimise   waves(work items over 148 SMs) x (k-blocks per item x per-k-block cost
@@ -504,8 +574,8 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   const int n_out = g.act == 2 ? g.N / 2 : g.N;
   int bn, splits;
   pick_tile(g.M, g.N, g.K, g.act, sc->num_sms, &bn, &splits);
-  CUtensorMap c;  // epilogue chunks: 64 columns (128B swizzle) or, for BN = 160, 32 columns (64B swizzle)
-  if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, bn % 64 == 0 ? 64 : 32)) return -1;
+  CUtensorMap c;  // epilogue chunks: 32 rows x 32 columns (64-byte rows, 64B swizzle)
+  if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) return -1;
   g.num_m = (g.M + BM - 1) / BM;
   g.num_n = g.N / bn;
   g.splits = splits;
