@@ -101,7 +101,9 @@ class TGUNet:
         dev = self.device
 
         def g(name):
-            return sd[name].to(device=dev, dtype=torch.float16).contiguous()
+            t = sd[name].to(device=dev, dtype=torch.float16).contiguous()
+            # TMA descriptors / 16-byte vector loads need 16-byte aligned bases (views into a flat broadcast buffer are not)
+            return t.clone() if t.data_ptr() % 16 else t
 
         w = {}
         w["conv_in.w"], w["conv_in.b"] = g("conv_in.weight"), g("conv_in.bias")
