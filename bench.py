@@ -14,6 +14,10 @@ One bench "step" is one timestep index of a turn:
       composite, capture of the 4 guidance attention maps + guidance energy for index < 30)  = 1 denoise step
 so value = 5 * K / seconds (x ranks; every rank owns independent dialogues -> weak scaling, no data-path
 collective; the UNet/IP weights are NCCL-broadcast from rank 0 once at start-up).
+By default the five trajectories share ONE UNet forward of batch 10 (per-sample IP scale; composite, capture and
+energy apply to the stage-2 trajectory only): in steady state a rank always holds a turn in stage 1 and another
+dialogue's turn in stage 2 (config 5: 8 dialogues per GPU), and co-batching them is a scheduling decision, not a
+change of arithmetic.  `--separate-stage2` runs the two forwards as separate graphs (B=8 then B=2) instead.
 ControlNet residuals of stage 2 are outside this round's scope and are not computed.
 """
 import argparse
@@ -205,12 +209,56 @@ def run_ours(args):
                 plan.run([self.captured[k][0] for k in KEYS], loss, ws)
 
     g2e, g2 = Stage2(True).capture(), Stage2(False).capture()
+    from theatergen_b200.engine import MixedStepGraph
+    mixed = not args.separate_stage2
+    gme = gm = None
+    if mixed:
+        gme = MixedStepGraph(eng, K, 1, 81, KEYS, plan).capture()
+        gm = MixedStepGraph(eng, K, 1, 81, None, None).capture()
+        for g in (gme, gm):
+            g.ctx.copy_(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
+            g.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4, 0.1] * 2))
+            g.latents.copy_(torch.cat([lat1, lat2]))
+            g.mask.copy_(h_mask)
+        h_ctxm = pin(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
+        h_latm = pin(torch.cat([lat1, lat2]))
+        h_tsm = pin(ts.cpu()[:, None].repeat(1, 2 * (K + 1)))
+        h_outm = torch.empty((K + 1, 4, 64, 64), dtype=torch.float16).pin_memory()
     g1.ctx.copy_(h_ctx1); g1.ip_scale.copy_(scale1); g1.latents.copy_(h_lat1)
     for g in (g2e, g2):
         g.ctx.copy_(h_ctx2); g.ip_scale.fill_(0.1); g.latents.copy_(h_lat2); g.mask.copy_(h_mask)
     torch.cuda.synchronize()
     launches_per_step = {True: g1.launches_per_step + g2e.launches_per_step,
                          False: g1.launches_per_step + g2.launches_per_step}
+    if mixed:
+        launches_per_step = {True: gme.launches_per_step, False: gm.launches_per_step}
+
+    def step_device_mixed(i):
+        idx = i % STEPS
+        g = gme if idx < 30 else gm
+        g.t.copy_(d_ts[idx].expand(2 * (K + 1))); g.coef.copy_(d_coef[idx]); g.frozen.copy_(d_frozen[idx + 1])
+        g.replay()
+        if idx == STEPS - 1:
+            gme.latents.copy_(h_latm, non_blocking=True)
+        elif idx == 29:
+            gm.latents.copy_(gme.latents)
+
+    def step_e2e_mixed(i):
+        idx = i % STEPS
+        g = gme if idx < 30 else gm
+        if idx == 0:
+            gme.ctx.copy_(h_ctxm, non_blocking=True); gm.ctx.copy_(h_ctxm, non_blocking=True)
+            gme.latents.copy_(h_latm, non_blocking=True); gme.mask.copy_(h_mask, non_blocking=True)
+            gm.mask.copy_(h_mask, non_blocking=True)
+        g.t.copy_(h_tsm[idx], non_blocking=True); g.coef.copy_(h_coef[idx], non_blocking=True)
+        g.frozen.copy_(h_frozen[idx + 1], non_blocking=True)
+        g.replay()
+        if idx == 29:
+            gm.latents.copy_(gme.latents)
+        h_outm.copy_(g.trace, non_blocking=True)
+        if idx < 30:
+            h_loss.copy_(gme.loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     def step_device(i):
         """inputs resident in HBM; only device-side work"""
@@ -276,21 +324,40 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device, Kb, Wb)
+    ms_dev = timed(step_device_mixed if mixed else step_device, Kb, Wb)
     clocks = sampler.stop() if rank == 0 else None
     n_energy = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) < 30)
     gpu_launches = n_energy * launches_per_step[True] + (Kb - n_energy) * launches_per_step[False]
-    ms_e2e = timed(step_e2e, Kb, Wb)
+    ms_e2e = timed(step_e2e_mixed if mixed else step_e2e, Kb, Wb)
+
+    # ---- replay time of each captured graph on its own (where the step time goes) ----
+    def graph_ms(g, n=10):
+        for _ in range(2):
+            g.replay()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(n):
+            g.replay()
+        e_.record()
+        torch.cuda.synchronize()
+        return round(s_.elapsed_time(e_) / n, 4)
+    graphs = None
+    if rank == 0:
+        graphs = {"stage1_B8": graph_ms(g1), "stage2_B2_capture_energy": graph_ms(g2e), "stage2_B2": graph_ms(g2)}
+        if mixed:
+            graphs.update({"cobatched_B10_capture_energy": graph_ms(gme), "cobatched_B10": graph_ms(gm)})
 
     # ---- roofline leg: every kernel family timed with CUDA events (eager, same shapes, same stream) ----
     roof, breakdown = None, None
     if rank == 0:
         net.ip_scale_per_sample = None
+        gp = gme if mixed else g1
         for _ in range(2):
-            g1._body()
+            gp._body()
         with ops.profile() as rec:
             for _ in range(3):
-                g1._body()
+                gp._body()
         rec.finish()
         summ = rec.summary()
         tot = sum(v["ms"] for v in summ.values())
@@ -324,13 +391,14 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "denoise_steps_per_bench_step_per_gpu": K + 1,
                        "l2_policy": "inputs larger than L2 (1.76 GB of weights streamed per forward vs 126 MB L2)",
-                       "cuda_graphs": True, "controlnet": "not computed (out of scope this round)",
+                       "cuda_graphs": True, "cobatch_stage1_stage2": mixed, "controlnet": "not computed (out of scope this round)",
                        "parallelism": f"dp{world} (independent dialogues per rank, weights NCCL-broadcast once)"},
             "e2e": {"value": round(e2e, 2), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / Kb, 4)},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
             "tensor_frac_of_step": round(value / world * FLOPS_PER_DENOISE_STEP / 1e12 / peaks()[0], 4),
-            "roofline": roof, "cpu_baseline": cpu, "kernel_breakdown_stage1_B8": breakdown,
+            "roofline": roof, "cpu_baseline": cpu, "graph_replay_ms": graphs,
+            "kernel_breakdown_per_forward": breakdown,
         }
         print(json.dumps(out))
     if world > 1:
@@ -344,6 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--separate-stage2", action="store_true", help="stage-1 (B=8) and stage-2 (B=2) as separate forwards")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

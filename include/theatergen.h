@@ -114,9 +114,12 @@ int tg_duplicate_latents(const tg_half* lat, tg_half* out, int n, void* stream);
  *   eps [2K,C,H,W] (rows [0,K) unconditional), latents [K,C,H,W] in/out, coef_dev = device float[5]
  *   {guidance_scale, sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)}; frozen [K,C,H,W] and mask [H,W]
  *   may be NULL (stage 1); latents_copy (nullable) receives a second copy (the latents_all trace).
+ *   pair_stride: rows between a trajectory's unconditional and conditional eps (0 = K).  A call may cover a sub-range
+ *   of a larger co-batch: pass eps + k0*C*HW, latents + k0*C*HW, K = count, pair_stride = K_total.
  * Replaces models/pipelines.py:441-447 and :820-834 + diffusers DDIMScheduler.step. */
 int tg_cfg_ddim_composite(const tg_half* eps, tg_half* latents, const float* coef_dev, const tg_half* frozen,
-                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, void* stream);
+                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, int pair_stride,
+                          void* stream);
 
 /* Cross-attention guidance energy, utils/guidance.py:244-286 (compute_ca_lossv3) with :91-148 (top-k box
  * energy) and :150-242 (reference-attention transfer).  All descriptor arrays are HOST memory and are passed

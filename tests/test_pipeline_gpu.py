@@ -156,3 +156,40 @@ def test_full_config_properties():
     assert torch.equal(out[0][:, mask.bool()], frozen[50, 0][:, mask.bool()])
     out30 = eng.denoise(lat[:1], ctx[[0, K]], 0.1, 50, frozen_all=frozen, frozen_mask=mask, frozen_steps=30)
     assert not torch.equal(out30[0][:, mask.bool()], frozen[50, 0][:, mask.bool()])
+
+
+def test_cobatched_stage1_stage2_step_matches_separate_steps():
+    """MixedStepGraph: 4 stage-1 trajectories + 1 stage-2 trajectory in one B=10 forward == the two separate steps
+    (same arithmetic per trajectory; only fp32 summation order may differ with the batch-dependent tile shapes)."""
+    OU, sd, net, adapter = _make()
+    from theatergen_b200.engine import DenoiseEngine, MixedStepGraph
+    from theatergen_b200.utils.guidance import EnergyPlan
+    eng = DenoiseEngine(net, adapter.pipe.scheduler, use_graphs=False)
+    g = torch.Generator().manual_seed(9)
+    K = 4
+    lat1, lat2 = torch.randn(K, 4, 64, 64, generator=g).half().cuda(), torch.randn(1, 4, 64, 64, generator=g).half().cuda()
+    ctx1, ctx2 = torch.randn(2 * K, 81, 768, generator=g).half().cuda(), torch.randn(2, 81, 768, generator=g).half().cuda()
+    frozen = torch.randn(1, 4, 64, 64, generator=g).half().cuda()
+    mask = torch.zeros(64, 64, device="cuda")
+    mask[8:40, 16:56] = 1
+    keys = [("mid", 0, 0, 0), ("up", 1, 0, 0)]
+    plan = EnergyPlan([[0.1, 0.2, 0.6, 0.7]], [[3, 4]], keys, fg_weight=1.0, bg_weight=4.0)
+    ts, coef = eng.tables(50, 7.5)
+    mx = MixedStepGraph(eng, K, 1, 81, keys, plan)
+    mx.latents.copy_(torch.cat([lat1, lat2])); mx.ctx.copy_(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
+    mx.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4, 0.1] * 2)); mx.frozen.copy_(frozen); mx.mask.copy_(mask.half())
+    mx.t.copy_(ts[3].expand(10)); mx.coef.copy_(coef[3])
+    mx._body()
+    s1 = eng.step_graph(K, 81, False)
+    s1.latents.copy_(lat1); s1.ctx.copy_(ctx1); s1.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2))
+    s1.t.copy_(ts[3].expand(8)); s1.coef.copy_(coef[3]); s1._body()
+    s2 = eng.step_graph(1, 81, True, keys)
+    s2.latents.copy_(lat2); s2.ctx.copy_(ctx2); s2.ip_scale.fill_(0.1); s2.frozen.copy_(frozen); s2.mask.copy_(mask.half())
+    s2.t.copy_(ts[3].expand(2)); s2.coef.copy_(coef[3]); s2._body()
+    assert (mx.latents[:K].float() - s1.latents.float()).abs().max().item() < 1e-2
+    assert (mx.latents[K:].float() - s2.latents.float()).abs().max().item() < 1e-2
+    assert torch.equal(mx.latents[K][:, mask.bool()], frozen[0][:, mask.bool()])
+    assert torch.equal(mx.trace, mx.latents)
+    loss2 = torch.zeros(1, device="cuda")
+    plan.run([s2.captured[k][0] for k in keys], loss2, torch.empty(256, device="cuda"))
+    assert abs(mx.loss.item() - loss2.item()) < 2e-3 * max(1.0, abs(loss2.item()))

@@ -33,7 +33,7 @@ _SIGS = {
     "tg_add_inplace": (ci, [vp, vp, C.c_longlong, vp]),
     "tg_nchw_to_nhwc": (ci, [vp, vp, ci, ci, ci, vp]),
     "tg_duplicate_latents": (ci, [vp, vp, ci, vp]),
-    "tg_cfg_ddim_composite": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp]),
+    "tg_cfg_ddim_composite": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, vp, ci, vp]),
     "tg_guidance_energy": (ci, [vp, vp, vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, vp, ci, cf, cf, cf, cf, cf, cf,
                                 vp, vp, vp]),
 }

@@ -104,9 +104,11 @@ int tg_duplicate_latents(const tg_half* lat, tg_half* out, int n, void* stream) 
   return tg::duplicate_latents(H(lat), HM(out), n, ST(stream));
 }
 int tg_cfg_ddim_composite(const tg_half* eps, tg_half* latents, const float* coef_dev, const tg_half* frozen,
-                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, void* stream) {
+                          const tg_half* mask, int K, int C, int HW, tg_half* latents_copy, int pair_stride,
+                          void* stream) {
   TG_CHECK(eps && latents && coef_dev && ((frozen == nullptr) == (mask == nullptr)), "tg_cfg_ddim_composite: bad arguments");
-  return tg::cfg_ddim_composite(H(eps), HM(latents), coef_dev, H(frozen), H(mask), K, C, HW, HM(latents_copy), ST(stream));
+  return tg::cfg_ddim_composite(H(eps), HM(latents), coef_dev, H(frozen), H(mask), K, C, HW, HM(latents_copy), pair_stride,
+                                ST(stream));
 }
 
 int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const int* map_hw, int n_keys,

@@ -74,6 +74,8 @@ template <int D, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 attn_self_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V, int ldq,
                  int ldk, int ldv, __half* __restrict__ O, int ldo, int Nq, int Nk, float scale_log2) {
+  grid_dep_launch();
+  grid_dep_wait();
   using Cfg = SelfCfg<D, NWARPS>;
   constexpr int DP = Cfg::DP, PITCH = Cfg::PITCH, BQ = Cfg::BQ, BKV = Cfg::BKV, NT = NWARPS * 32;
   constexpr int KSTEPS = DP / 16;     // k16 steps over the head dim for S = Q K^T
@@ -235,7 +237,7 @@ static int launch_self(const __half* Q, const __half* K, const __half* V, int ld
     attr = true;
   }
   dim3 grid((Nq + Cfg::BQ - 1) / Cfg::BQ, heads, B);
-  kern<<<grid, NWARPS * 32, Cfg::SMEM, st>>>(Q, K, V, ldq, ldk, ldv, O, ldo, Nq, Nk, scale * 1.4426950408889634f);
+  TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, K, V, ldq, ldk, ldv, O, ldo, Nq, Nk, scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -382,6 +384,8 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
                      int ldkv, int n_text, int n_ip, const float* __restrict__ ip_scale,
                      const __half* __restrict__ add_mask, __half* __restrict__ O, int ldo,
                      __half* __restrict__ probs, int probs_b0, int Nq, float scale_log2) {
+  grid_dep_launch();
+  grid_dep_wait();
   using Cfg = CrossCfg<D, NWARPS>;
   constexpr int DP = Cfg::DP, PITCH = Cfg::PITCH, BQ = Cfg::BQ, NT = NWARPS * 32, DT = (D + 7) / 8;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -453,8 +457,8 @@ static int launch_cross(const __half* Q, int ldq, const __half* Kt, const __half
     attr = true;
   }
   dim3 grid((Nq + Cfg::BQ - 1) / Cfg::BQ, heads, B);
-  kern<<<grid, NWARPS * 32, Cfg::SMEM, st>>>(Q, ldq, Kt, Vt, Ki, Vi, ldkv, n_text, n_ip, ip_scale, add_mask, O, ldo,
-                                             probs, probs_b0, Nq, scale * 1.4426950408889634f);
+  TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, ldq, Kt, Vt, Ki, Vi, ldkv, n_text, n_ip, ip_scale, add_mask, O, ldo,
+                                             probs, probs_b0, Nq, scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

@@ -111,6 +111,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  grid_dep_launch();  // PDL: the prologue above overlapped the previous kernel's tail
+  grid_dep_wait();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + 128;  // S[2] at +0,+64 ; O (single, accumulated) at +128
 
@@ -299,10 +301,9 @@ int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int
   if (make_tmap_2d(&tq, Q, rows, cols, ldq, ATQ)) return -1;
   if (make_tmap_2d(&tk, K, rows, cols, ldk, ATK)) return -1;
   if (make_tmap_2d(&tv, V, rows, cols, ldv, ATK)) return -1;
-  attn_tc_kernel<<<dim3(N / ATQ, heads, B), 192, AT_SMEM, st>>>(tq, tk, tv, O, ldo, N, d,
-                                                               scale * 1.4426950408889634f);
+  TG_CUDA(launch_kernel(attn_tc_kernel, dim3(N / ATQ, heads, B), dim3(192), AT_SMEM, st, 1, tq, tk, tv, O, ldo, N, d,
+                        scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
-  TG_LAUNCH_CHECK();
   return 0;
 }
 

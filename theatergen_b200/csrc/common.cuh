@@ -208,6 +208,11 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Programmatic dependent launch: let the next kernel in the stream get scheduled (and run its prologue) while this
+// one is still running; every kernel waits for its prerequisite grids before touching global memory.
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 // exact-GELU without MUFU: erf(z) = z * P(z^2) on [0, 3.2] (degree-8 least-squares fit at Chebyshev nodes, |err| < 9e-5,
@@ -240,6 +245,40 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 #endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------------------------
+// host: kernel launch with programmatic stream serialization (PDL) and optional thread-block clusters
+// ----------------------------------------------------------------------------------------------
+bool pdl_enabled();  // TG_PDL=0 disables (A/B testing)
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // host: TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)

@@ -214,6 +214,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   __syncthreads();
   if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
   tc_fence_after();
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
+  grid_dep_launch();
+  grid_dep_wait();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -501,19 +504,7 @@ static int launch_gemm_impl(const CUtensorMap& a1, const CUtensorMap& a2, const 
   const int work = rows_m * g.num_n * g.splits;
   const int max_workers = MC ? sc.num_sms / 2 : sc.num_sms;
   const int workers = work < max_workers ? work : max_workers;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(MC ? 2 * workers : workers);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = L::TOTAL;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = MC ? 2 : 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  TG_CUDA(cudaLaunchKernelEx(&cfg, kern, a1, a2, b, c, g));
+  TG_CUDA(launch_kernel(kern, dim3(MC ? 2 * workers : workers), dim3(NUM_THREADS), L::TOTAL, st, MC ? 2 : 1, a1, a2, b, c, g));
   TG_COUNT_LAUNCH();
   return 0;
 }
@@ -532,9 +523,10 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __hal
   return launch_gemm_impl<BN, STAGES, false>(a1, a2, Wt, c, g, sc, st);
 }
 
-// Tile width / split choice: minimise   waves(work items over 148 SMs) x (k-blocks per item x per-k-block cost
-// + epilogue).  Per k-block (128 x BN x 64): tensor pipe 2*BN cycles, smem->tensor feed (16 KB + 128*BN B) at
-// 128 B/clk = 128 + BN cycles.  Wider tiles raise flop/byte; split-K fills the SMs when M is small and K long.
+// Tile width / split choice: minimise   waves(work items over the SMs) x (k-blocks per item x per-k-block cost +
+// epilogue).  Measured on B200: a 128 x BN x 64 k-block is bound by the SM's shared-memory ingest (~51 B/clk, i.e.
+// (16 KB + 128*BN B) / 51 cycles) long before the tensor pipe (2*BN cycles), so wider tiles are always cheaper per
+// flop and wave quantisation decides the rest; split-K fills the SMs when M is small and K long.
 static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out) {
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
   const int cands[5] = {256, 192, 160, 128, 64};
@@ -555,8 +547,9 @@ static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, in
       while (s > 1 && ((size_t)tiles * s * BM * bn * 4 > SPLITK_WS_BYTES || tiles > SPLITK_MAX_TILES)) --s;
     }
     const int waves = (tiles * s + num_sms - 1) / num_sms;
-    const double per_kb = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
-    const double epi = 400.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
+    const double ingest = (16384.0 + 128.0 * bn) / 51.0;
+    const double per_kb = (2.0 * bn > ingest) ? 2.0 * bn : ingest;
+    const double epi = 1500.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
     const double cost = waves * (per_kb * ((nk + s - 1) / s) + epi);
     if (cost < best_cost * 0.999) {
       best_cost = cost;

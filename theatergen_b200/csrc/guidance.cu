@@ -52,6 +52,8 @@ __device__ __forceinline__ float warp_topk_sum(const uint32_t (&bits)[PER], int 
 
 __global__ void __launch_bounds__(256)
 guidance_energy_kernel(const GuidanceParams P, float* __restrict__ partial) {
+  grid_dep_launch();
+  grid_dep_wait();
   const GuidanceItem it = P.items[blockIdx.x];
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = P.map_hw[it.key];
@@ -142,6 +144,8 @@ guidance_energy_kernel(const GuidanceParams P, float* __restrict__ partial) {
 // reference-attention transfer term: mean_heads sum_px | A m / (sum A m + eps) - R m / (sum R m + eps) |
 __global__ void __launch_bounds__(256)
 guidance_ref_kernel(const GuidanceParams P, float* __restrict__ partial) {
+  grid_dep_launch();
+  grid_dep_wait();
   const GuidanceItem it = P.ref_items[blockIdx.x];
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW = P.map_hw[it.key];
@@ -184,6 +188,8 @@ guidance_ref_kernel(const GuidanceParams P, float* __restrict__ partial) {
 }
 
 __global__ void guidance_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ loss) {
+  grid_dep_launch();
+  grid_dep_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < n; ++i) s += partial[i];
@@ -197,16 +203,16 @@ int guidance_energy(const GuidanceParams& P, float* loss_out, float* workspace, 
            "guidance: too many keys/boxes/items");
   for (int k = 0; k < P.n_keys; ++k) TG_CHECK(P.map_hw[k] <= GUIDANCE_MAX_HW, "guidance: map HW %d > %d", P.map_hw[k], GUIDANCE_MAX_HW);
   if (P.n_items > 0) {
-    guidance_energy_kernel<<<P.n_items, 256, 0, st>>>(P, workspace);
+    TG_CUDA(launch_kernel(guidance_energy_kernel, dim3(P.n_items), dim3(256), 0, st, 1, P, workspace));
     TG_COUNT_LAUNCH();
     TG_LAUNCH_CHECK();
   }
   if (P.n_ref_items > 0) {
-    guidance_ref_kernel<<<P.n_ref_items, 256, 0, st>>>(P, workspace);
+    TG_CUDA(launch_kernel(guidance_ref_kernel, dim3(P.n_ref_items), dim3(256), 0, st, 1, P, workspace));
     TG_COUNT_LAUNCH();
     TG_LAUNCH_CHECK();
   }
-  guidance_final_kernel<<<1, 32, 0, st>>>(workspace, P.n_items + P.n_ref_items, loss_out);
+  TG_CUDA(launch_kernel(guidance_final_kernel, dim3(1), dim3(32), 0, st, 1, workspace, P.n_items + P.n_ref_items, loss_out));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

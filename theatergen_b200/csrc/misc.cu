@@ -10,6 +10,8 @@ namespace tg {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8, size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8);
     size_t p = i / C8;
@@ -25,8 +27,8 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cuda
   TG_CHECK(C % 8 == 0, "upsample: C %% 8 != 0");
   const size_t total = (size_t)B * 4 * H * W * (C / 8);
   const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
-  upsample2x_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C / 8,
-                                          total);
+  TG_CUDA(launch_kernel(upsample2x_kernel, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), H, W, C / 8,
+                                          total));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -38,6 +40,8 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cuda
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int H, int W, int C8, size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int Ho = H / 2, Wo = W / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8);
@@ -59,8 +63,8 @@ int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaS
   TG_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad dims");
   const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
   const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
-  im2col_s2_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(a), H, W, C / 8,
-                                         total);
+  TG_CUDA(launch_kernel(im2col_s2_kernel, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(a), H, W, C / 8,
+                                         total));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -74,6 +78,8 @@ template <int CIN, int PIX>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                __half* __restrict__ y, int H, int W, int Cout) {
+  grid_dep_launch();
+  grid_dep_wait();
   extern __shared__ float sm_ci[];
   float* sw = sm_ci;                        // [CIN*9][Cout]
   float* sp = sw + CIN * 9 * Cout;          // [PIX][CIN*9]
@@ -112,7 +118,7 @@ int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, _
     attr = true;
   }
   TG_CHECK(smem <= 96 * 1024, "conv_in: Cout=%d too large", Cout);
-  kern<<<dim3((H * W + PIX - 1) / PIX, B), 256, smem, st>>>(x, w, bias, y, H, W, Cout);
+  TG_CUDA(launch_kernel(kern, dim3((H * W + PIX - 1) / PIX, B), dim3(256), smem, st, 1, x, w, bias, y, H, W, Cout));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -126,6 +132,8 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                 __half* __restrict__ y, int B, int H, int W, int C) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int HW = H * W;
   if (warp >= B * HW) return;
@@ -158,7 +166,7 @@ int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, 
                           cudaStream_t st) {
   TG_CHECK(C % 2 == 0, "conv_out: C odd");
   const int warps = B * H * W;
-  conv_out_kernel<4><<<(warps * 32 + 255) / 256, 256, 0, st>>>(x, w, bias, y, B, H, W, C);
+  TG_CUDA(launch_kernel(conv_out_kernel<4>, dim3((warps * 32 + 255) / 256), dim3(256), 0, st, 1, x, w, bias, y, B, H, W, C));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -170,6 +178,8 @@ int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, 
 // captured CUDA graph can be replayed for every timestep.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, __half* __restrict__ out, int dim) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.x, half_dim = dim / 2;
   const float tv = t[b];
   for (int i = threadIdx.x; i < half_dim; i += blockDim.x) {
@@ -181,7 +191,7 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, __half* __res
 }
 
 int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st) {
-  timestep_embed_kernel<<<B, 160, 0, st>>>(t_dev, out, dim);
+  TG_CUDA(launch_kernel(timestep_embed_kernel, dim3(B), dim3(160), 0, st, 1, t_dev, out, dim));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -189,13 +199,15 @@ int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStre
 
 // y += x (ControlNet residual adds, ip_adapter/unet_2d_condition.py:1044-1053, 1077-1078)
 __global__ void __launch_bounds__(256) add_inplace_kernel(__half2* __restrict__ y, const __half2* __restrict__ x, size_t n2) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x)
     y[i] = __hadd2(y[i], x[i]);
 }
 int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st) {
   TG_CHECK(n % 2 == 0, "add: odd length");
   const int grid = (int)(((n / 2 + 255) / 256) < (size_t)(148 * 8) ? ((n / 2 + 255) / 256) : (size_t)(148 * 8));
-  add_inplace_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<__half2*>(y), reinterpret_cast<const __half2*>(x), n / 2);
+  TG_CUDA(launch_kernel(add_inplace_kernel, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<__half2*>(y), reinterpret_cast<const __half2*>(x), n / 2));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -204,6 +216,8 @@ int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st) {
 // NCHW <-> NHWC for the (tiny) ControlNet residual interface
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C, int HW, size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const size_t p = i / C;
@@ -215,7 +229,7 @@ nchw_to_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ y, int C,
 int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t st) {
   const size_t total = (size_t)B * C * HW;
   const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
-  nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(x, y, C, HW, total);
+  TG_CUDA(launch_kernel(nchw_to_nhwc_kernel, dim3(grid), dim3(256), 0, st, 1, x, y, C, HW, total));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -232,13 +246,15 @@ int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t 
 __global__ void __launch_bounds__(256)
 cfg_ddim_kernel(const __half* __restrict__ eps, __half* __restrict__ lat, const float* __restrict__ coef,
                 const __half* __restrict__ frozen, const __half* __restrict__ mask, int K, int CHW, int HW,
-                __half* __restrict__ lat_copy) {
+                __half* __restrict__ lat_copy, int pair_stride) {
+  grid_dep_launch();
+  grid_dep_wait();
   const float g = coef[0], sa = coef[1], s1a = coef[2], sap = coef[3], s1ap = coef[4];
   const int total = K * CHW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / CHW, r = i % CHW;
     const float eu = __half2float(eps[(size_t)k * CHW + r]);
-    const float ec = __half2float(eps[(size_t)(K + k) * CHW + r]);
+    const float ec = __half2float(eps[(size_t)(pair_stride + k) * CHW + r]);
     // every intermediate of the reference is an fp16 tensor (fp32 python/0-d scalars do not promote)
     const float e = __half2float(__float2half_rn(eu + g * (ec - eu)));
     const float x = __half2float(lat[i]);
@@ -255,10 +271,12 @@ cfg_ddim_kernel(const __half* __restrict__ eps, __half* __restrict__ lat, const 
 }
 
 int cfg_ddim_composite(const __half* eps, __half* latents, const float* coef_dev, const __half* frozen,
-                       const __half* mask, int K, int C, int HW, __half* latents_copy, cudaStream_t st) {
+                       const __half* mask, int K, int C, int HW, __half* latents_copy, int pair_stride,
+                       cudaStream_t st) {
+  if (pair_stride <= 0) pair_stride = K;
   const int total = K * C * HW;
-  cfg_ddim_kernel<<<(total + 255) / 256, 256, 0, st>>>(eps, latents, coef_dev, frozen, mask, K, C * HW, HW,
-                                                       latents_copy);
+  TG_CUDA(launch_kernel(cfg_ddim_kernel, dim3((total + 255) / 256), dim3(256), 0, st, 1, eps, latents, coef_dev, frozen, mask, K, C * HW, HW,
+                        latents_copy, pair_stride));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -267,6 +285,8 @@ int cfg_ddim_composite(const __half* eps, __half* latents, const float* coef_dev
 // duplicate latents for CFG: x_in[2K] = cat([latents]*2) (models/pipelines.py:409, 747)
 __global__ void __launch_bounds__(256)
 dup_kernel(const __half* __restrict__ lat, __half* __restrict__ out, int n) {
+  grid_dep_launch();
+  grid_dep_wait();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const __half v = lat[i];
     out[i] = v;
@@ -274,7 +294,7 @@ dup_kernel(const __half* __restrict__ lat, __half* __restrict__ out, int n) {
   }
 }
 int duplicate_latents(const __half* lat, __half* out, int n, cudaStream_t st) {
-  dup_kernel<<<(n + 255) / 256, 256, 0, st>>>(lat, out, n);
+  TG_CUDA(launch_kernel(dup_kernel, dim3((n + 255) / 256), dim3(256), 0, st, 1, lat, out, n));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

@@ -26,6 +26,8 @@ static constexpr int GN_MAX_BATCH = 256;
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
                 float* __restrict__ partial, float* __restrict__ stats, int* __restrict__ counters, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.y, slab = blockIdx.x;
   const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
   const int rows_per = (HW + slabs - 1) / slabs;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
                 const float* __restrict__ stats, const __half* __restrict__ gamma,
                 const __half* __restrict__ beta, int silu, __half* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int b = blockIdx.y, slab = blockIdx.x;
   const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
   const int R = GN_THREADS / c8n;
@@ -186,12 +190,12 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   int* counters = reinterpret_cast<int*>(workspace);
   float* stats = workspace + GN_MAX_BATCH;
   float* partial = stats + (size_t)GN_MAX_BATCH * GN_GROUPS * 2;
-  gn_stats_kernel<<<dim3(slabs, B), GN_THREADS, smem, st>>>(x1, C1, x2, C2, HW, slabs, partial, stats, counters, eps);
+  TG_CUDA(launch_kernel(gn_stats_kernel, dim3(slabs, B), dim3(GN_THREADS), smem, st, 1, x1, C1, x2, C2, HW, slabs, partial, stats, counters, eps));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   int aslabs = (8 * 148 + B - 1) / B;  // ~8 CTAs per SM in flight, >= 4 rows per row-lane
   aslabs = max(1, min(aslabs, HW / max(1, 4 * R)));
-  gn_apply_kernel<<<dim3(aslabs, B), GN_THREADS, 0, st>>>(x1, C1, x2, C2, HW, aslabs, stats, gamma, beta, silu, out);
+  TG_CUDA(launch_kernel(gn_apply_kernel, dim3(aslabs, B), dim3(GN_THREADS), 0, st, 1, x1, C1, x2, C2, HW, aslabs, stats, gamma, beta, silu, out));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -204,6 +208,8 @@ template <int PER_LANE>  // half2 per lane: C = 64 * PER_LANE
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, int ldx, const __half* __restrict__ gamma,
                  const __half* __restrict__ beta, float eps, __half* __restrict__ out, int ldo, int M) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -242,7 +248,7 @@ int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* 
   dim3 grid((M + warps - 1) / warps);
 #define TG_LN(P)                                                                                    \
   case P:                                                                                           \
-    layernorm_kernel<P><<<grid, warps * 32, 0, st>>>(x, ldx, gamma, beta, eps, out, ldo, M);        \
+    TG_CUDA(launch_kernel(layernorm_kernel<P>, dim3(grid), dim3(warps * 32), 0, st, 1, x, ldx, gamma, beta, eps, out, ldo, M));        \
     break;
   switch (C / 64) {
     TG_LN(5) TG_LN(10) TG_LN(12) TG_LN(16) TG_LN(20) TG_LN(24)

@@ -57,7 +57,8 @@ int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStre
 int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st);
 int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t st);
 int cfg_ddim_composite(const __half* eps, __half* latents, const float* coef_dev, const __half* frozen,
-                       const __half* mask, int K, int C, int HW, __half* latents_copy, cudaStream_t st);
+                       const __half* mask, int K, int C, int HW, __half* latents_copy, int pair_stride,
+                       cudaStream_t st);
 int duplicate_latents(const __half* lat, __half* out, int n, cudaStream_t st);
 
 // ---- guidance energy (guidance.cu); the whole description travels as a kernel parameter (graph capturable) ----

@@ -65,6 +65,35 @@ class StepGraph:
         self.graph.replay()
 
 
+class MixedStepGraph(StepGraph):
+    """One denoise step for a co-batch of K1 stage-1 trajectories (plain CFG + DDIM) and K2 stage-2 trajectories
+    (masked composite, optional capture of the guidance maps + energy): independent trajectories of different
+    turns / dialogues that happen to sit at the same timestep index share ONE UNet forward of batch 2*(K1+K2) with
+    per-sample IP scale.  `energy_plan` (utils.guidance.EnergyPlan) is evaluated on the first stage-2 trajectory."""
+
+    def __init__(self, engine, K1, K2, T, capture_keys=None, energy_plan=None):
+        super().__init__(engine, K1 + K2, T, False, capture_keys)
+        dev = engine.device
+        self.K1, self.K2 = K1, K2
+        self.frozen = torch.zeros((K2, 4, 64, 64), dtype=torch.float16, device=dev)
+        self.mask = torch.zeros((64, 64), dtype=torch.float16, device=dev)
+        self.energy_plan = energy_plan
+        self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._ws = torch.empty((256,), dtype=torch.float32, device=dev)
+
+    def _body(self):
+        net = self.engine.unet
+        ops.duplicate_latents(self.latents, self.x_in)
+        eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
+                              save_keys=self.capture_keys, cond_only=True)
+        if self.energy_plan is not None:
+            self.energy_plan.run([self.captured[k][self.K1] for k in self.capture_keys], self.loss, self._ws)
+        K1, K2 = self.K1, self.K2
+        ops.cfg_ddim_composite(eps, self.latents, self.coef, latents_copy=self.trace[:K1], k0=0, count=K1)
+        ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
+                               latents_copy=self.trace[K1:], k0=K1, count=K2)
+
+
 class DenoiseEngine:
     def __init__(self, unet: TGUNet, scheduler: DDIMScheduler | None = None, use_graphs=True):
         self.unet = unet

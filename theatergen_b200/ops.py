@@ -275,12 +275,17 @@ def duplicate_latents(lat, out):
     return out
 
 
-def cfg_ddim_composite(eps, latents, coef_dev, frozen=None, mask=None, latents_copy=None):
-    """eps [2K,C,H,W], latents [K,C,H,W] updated in place; coef_dev float32[5] on device."""
+def cfg_ddim_composite(eps, latents, coef_dev, frozen=None, mask=None, latents_copy=None, k0=0, count=None):
+    """eps [2K,C,H,W], latents [K,C,H,W] updated in place; coef_dev float32[5] on device.
+    k0 / count restrict the update to trajectories [k0, k0+count) of the co-batch (frozen / latents_copy are then
+    [count,C,H,W])."""
     _chk16(eps, latents, frozen, mask, latents_copy)
     K, Cc, H, W = latents.shape
     assert eps.shape[0] == 2 * K and coef_dev.dtype == torch.float32 and coef_dev.numel() >= 5
-    rc = _lib.lib().tg_cfg_ddim_composite(_p(eps), _p(latents), _p(coef_dev), _p(frozen), _p(mask), K, Cc, H * W,
-                                          _p(latents_copy), _stream())
+    count = K - k0 if count is None else count
+    assert eps.is_contiguous() and latents.is_contiguous() and 0 <= k0 and k0 + count <= K
+    off = k0 * Cc * H * W * 2
+    rc = _lib.lib().tg_cfg_ddim_composite(_p(eps) + off, _p(latents) + off, _p(coef_dev), _p(frozen), _p(mask), count,
+                                          Cc, H * W, _p(latents_copy), K, _stream())
     _lib.check(rc, "tg_cfg_ddim_composite")
     return latents
