@@ -373,6 +373,32 @@ def run_ours(args):
                 "algorithmic_flops_per_launch": round(top[1]["flops"] / top[1]["launches"]),
                 "launches_timed": top[1]["launches"]}
 
+    # one representative launch of the dominant kernel, timed alone (burst peak applies): the 3x3 conv 320->320 at
+    # 64x64 for the co-batched batch of 10 (M = 40960, K = 2880); its DRAM traffic comes from the committed ncu capture
+    if rank == 0:
+        xb = torch.randn(10, 64, 64, 320, device=dev).half()
+        wb = (torch.randn(320, 3, 3, 320, device=dev) * 0.02).half()
+        ob = torch.empty(10, 64, 64, 320, device=dev, dtype=torch.float16)
+        for _ in range(3):
+            ops.conv3x3(xb, wb, out=ob)
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(20):
+            ops.conv3x3(xb, wb, out=ob)
+        e_.record()
+        torch.cuda.synchronize()
+        us = s_.elapsed_time(e_) / 20 * 1e3
+        fl = 2.0 * 40960 * 320 * 2880
+        burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
+        roof["representative_launch"] = {
+            "what": "conv3x3 320->320 @64x64, B=10 (gemm_tc_kernel<160,5>, CONV3 mode), timed alone, 20 launches",
+            "us": round(us, 2), "achieved": round(fl / us / 1e6, 1), "peak": burst, "unit": "TFLOP/s",
+            "frac": round(fl / us / 1e6 / burst, 4), "algorithmic_flops": fl,
+            "algorithmic_bytes": 2.0 * (40960 * 320 * 2 + 320 * 2880),
+            "traffic": "see profiles/r01c_full.md (dram__bytes_read+write of the captured launches)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         total, cores = cpu_denoise_steps(2, 1)
