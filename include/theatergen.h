@@ -66,6 +66,11 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream);
 
+/* Launch-geometry knobs of tg_groupnorm for measurements (values <= 0 keep the current setting; fused: 1 allows the
+ * single-kernel cluster path for tensors whose per-image slab fits on chip, 0 forces the two-pass kernels, <0 keeps).
+ * No reference counterpart (the reference leaves this to ATen). */
+int tg_groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused);
+
 /* row-wise LayerNorm (ip_adapter/attention.py:198,226,238; resampler.py:16,43-44,100; ip_adapter.py:39) */
 int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* beta, float eps, tg_half* out,
                  int ldo, int M, int C, void* stream);

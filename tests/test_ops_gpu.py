@@ -126,6 +126,32 @@ def test_groupnorm(B, HW, C1, C2, silu):
     _close(out, ref.transpose(1, 2), 4e-3, 4e-3, "groupnorm")
 
 
+@pytest.mark.parametrize("B,HW,C1,C2", [(10, 64, 1280, 1280), (10, 256, 1280, 0), (5, 1024, 640, 0), (3, 1024, 320, 0),
+                                        (10, 1024, 1280, 640), (3, 4096, 640, 320)])
+def test_groupnorm_paths_agree_and_are_batch_independent(B, HW, C1, C2):
+    """single-kernel cluster path vs two-pass kernels (forced through tg_groupnorm_tune) on the same input, and an
+    image's result must not depend on the batch it travels in (co-batched characters == solo)."""
+    from theatergen_b200 import _lib, ops
+    x1 = _rand((B, HW, C1), 1) + 0.5
+    x2 = _rand((B, HW, C2), 2, 2.0) if C2 else None
+    C = C1 + C2
+    gamma, beta = _rand((C,), 3) * 0.1 + 1, _rand((C,), 4, 0.1)
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.silu(F.group_norm(x.float().transpose(1, 2), 32, gamma.float(), beta.float(), 1e-5)).transpose(1, 2)
+    try:
+        outs = []
+        for fused in (1, 0):
+            _lib.lib().tg_groupnorm_tune(0, 0, fused)
+            out = ops.groupnorm(x1, gamma, beta, 1e-5, x2=x2, silu=True)
+            _close(out, ref, 4e-3, 4e-3, f"groupnorm fused={fused}")
+            solo = ops.groupnorm(x1[1:2].contiguous(), gamma, beta, 1e-5,
+                                 x2=None if x2 is None else x2[1:2].contiguous(), silu=True)
+            assert torch.equal(solo[0], out[1]), f"fused={fused}: result depends on the batch"
+            outs.append(out)
+    finally:
+        _lib.lib().tg_groupnorm_tune(0, 0, 1)
+
+
 @pytest.mark.parametrize("M,C", [(8192, 320), (2048, 640), (512, 1280), (273, 768), (5, 768)])
 def test_layernorm(M, C):
     from theatergen_b200 import ops

@@ -21,6 +21,7 @@ _SIGS = {
     "tg_gemm": (ci, [vp, ci, ci, vp, ci, vp, ci, ci, ci, vp, vp, ci, ci, vp, ci, ci, cf, vp, ci, vp]),
     "tg_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, cf, vp, ci, vp]),
     "tg_groupnorm": (ci, [vp, ci, vp, ci, ci, ci, vp, vp, cf, ci, vp, vp, vp]),
+    "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),
     "tg_attention": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, cf, vp]),
     "tg_attention_tc": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cf, vp]),

@@ -42,6 +42,11 @@ int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, in
   return tg::groupnorm_nhwc(H(x1), C1, H(x2), C2, B, HW, H(gamma), H(beta), eps, silu, HM(out), workspace, ST(stream));
 }
 
+int tg_groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused) {
+  tg::groupnorm_tune(stats_slabs, apply_ctas_per_sm, fused);
+  return 0;
+}
+
 int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* beta, float eps, tg_half* out,
                  int ldo, int M, int C, void* stream) {
   TG_CHECK(x && gamma && beta && out, "tg_layernorm: null pointer");

@@ -14,11 +14,14 @@
 // single-thread tcgen05.mma issuer, warps2..5 = epilogue.  The accumulator is double-buffered in TMEM
 // (2 x BN columns), so the epilogue of item i (TMEM -> registers -> bias/temb/activation/residual -> swizzled
 // smem -> TMA store) overlaps the main loop of item i+1.
-// TMA multicast (MC = true, used whenever there are >= 2 M-tiles): CTAs run as clusters of two that own vertically
-// adjacent 128-row tiles of the same N-tile; each CTA fetches half of the B (weight) tile and multicasts it into
-// both CTAs' shared memory, so the L2->SM traffic per CTA and k-block drops from 16 KB + 128*BN to 16 KB + 64*BN
-// (the smem->tensor feed, not the tensor pipe, is what bounds these tiles).  Every CTA still issues its own
-// 128 x BN tcgen05.mma; a stage is released to BOTH producers by a multicast tcgen05.commit.
+// CTA pairs (PAIR = true, used whenever there are >= 2 M-tiles): two CTAs of one TPC run as a cluster and own a
+// 256 x BN tile through tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages its own 128 rows of A and only HALF of
+// the B (weight) tile (BN/2 rows); the tensor cores of both SMs read both halves, so the L2->smem traffic per SM and
+// k-block drops from 16 KB + 128*BN to 16 KB + 64*BN bytes -- the smem ingest, not the tensor pipe, is what bounds a
+// single-CTA tile (measured ~51 B/clk/SM).  The leader CTA (cluster rank 0) issues every MMA; the TMA loads of both CTAs
+// complete on the leader's full barrier (cp.async.bulk.tensor .cta_group::2), a multicast tcgen05.commit releases the
+// smem slot / publishes the accumulator in BOTH CTAs, and the epilogue warps of both CTAs arrive on the leader's
+// accumulator-empty barrier through its shared::cluster address.  Each CTA runs the epilogue of its own 128 rows.
 // Split-K (small-M, long-K layers: the 8x8 / 16x16 levels stream 30-60 MB of weights through <= 40 tiles):
 // every split writes its fp32 partial tile to an L2-resident workspace, a per-tile semaphore elects the last
 // arriving CTA, which sums the partials in a FIXED order (bit-reproducible) and runs the fused epilogue.
@@ -57,10 +60,10 @@ struct GemmArgs {
   int* sem;    // split-K arrival counters, one per tile (self-resetting)
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool PAIR>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a CTA of a pair stages half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_BUF_BYTES;
@@ -74,19 +77,60 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                               uint16_t cta_mask) {
+// ---- CTA-pair (cta_group::2) flavours ----
+// shared::cluster address of the same shared-memory location in the cluster's CTA `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+// TMA loads whose completion bytes are signalled on an mbarrier that may live in the peer CTA (cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
-      "%4}], [%2], %5;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive (count 1) on the same barrier in every CTA of cta_mask once all previously issued pair-MMAs have retired
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
                "h"(cta_mask)
                : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -165,11 +209,11 @@ __device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[4]
   }
 }
 
-template <int BN, int STAGES, bool MC>
+template <int BN, int STAGES, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -183,11 +227,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int nk = g.K / BK;
   const int S = g.splits;
-  // MC: a cluster of two CTAs owns the M-tile pair (2*pm, 2*pm + 1); rank selects the tile and the B half it fetches
-  const int rank = MC ? (int)cluster_ctarank() : 0;
-  const int worker = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int num_workers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int rows_m = MC ? (g.num_m + 1) / 2 : g.num_m;  // M-tile rows of the work grid
+  // PAIR: a cluster of two CTAs owns the M-tile pair (2*pm, 2*pm + 1); rank selects the CTA's 128 rows and the half
+  // of the weight tile it stages.  Rank 0 is the leader (MMA issuer; owner of the full / accumulator-empty barriers).
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int rows_m = PAIR ? (g.num_m + 1) / 2 : g.num_m;  // M-tile rows of the work grid
   const int num_work = rows_m * g.num_n * S;
   constexpr uint32_t ACC_STRIDE = BN <= 128 ? 128 : 256;
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
@@ -198,21 +243,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: both CTAs' MMAs must have drained the slot
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_WARPS);
+      mbar_init(&acc_empty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // PAIR: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {  // the same warp of both CTAs: one allocation spanning the pair's two tensor memories
+      tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast into them
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
   grid_dep_launch();
@@ -227,7 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int cblk = g.mode == 1 ? g.Cin / BK : 1;
       for (int w = worker; w < num_work; w += num_workers) {
         const int wt = w / S, split = w - wt * S;
-        const int m0 = ((wt / g.num_n) * (MC ? 2 : 1) + rank) * BM, n0 = (wt % g.num_n) * BN;
+        const int m0 = ((wt / g.num_n) * (PAIR ? 2 : 1) + rank) * BM, n0 = (wt % g.num_n) * BN;
         const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
         int conv_b0 = 0, conv_y0 = 0;
         if (g.mode == 1) {
@@ -240,6 +290,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
+          if (PAIR) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+            if (g.mode == 0) {
+              const int k0 = kb * BK;
+              if (k0 < g.K1)
+                tma_load_2d_2sm(sa, &tmA1, fb, k0, m0);
+              else
+                tma_load_2d_2sm(sa, &tmA2, fb, k0 - g.K1, m0);
+            } else {
+              const int tap = kb / cblk;
+              const int c0 = (kb - tap * cblk) * BK;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_2sm(sa, &tmA1, fb, c0, kx - 1, conv_y0 + ky - 1, conv_b0);
+            }
+            tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0 + rank * (BN / 2));  // my half of the weight tile
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           if (g.mode == 0) {
             const int k0 = kb * BK;
@@ -253,17 +322,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             const int ky = tap / 3, kx = tap - ky * 3;
             tma_load_4d(sa, &tmA1, &full_bar[s], c0, kx - 1, conv_y0 + ky - 1, conv_b0);
           }
-          if (MC)  // my half of the weight tile, delivered to both CTAs of the pair
-            tma_load_2d_mc(sb + rank * (L::B_BYTES / 2), &tmB, &full_bar[s], kb * BK, n0 + rank * (BN / 2), 0x3);
-          else
-            tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN);
       int it = 0, j = 0;
       for (int w = worker; w < num_work; w += num_workers, ++j) {
         const int wt = w / S, split = w - wt * S;
@@ -283,14 +349,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
             const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
-            umma_f16_ss(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR)
+              umma_f16_ss_2sm(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16_ss(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (MC)
-            tc_commit_mc(&empty_bar[s], 0x3);  // the slot is written by both producers: release it to both
+          if (PAIR)
+            tc_commit_2sm(&empty_bar[s], 0x3);  // frees the slot in both CTAs when these MMAs retire
           else
-            tc_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+            tc_commit(&empty_bar[s]);
         }
-        tc_commit(&acc_full[as]);  // accumulator complete
+        if (PAIR)
+          tc_commit_2sm(&acc_full[as], 0x3);  // accumulator halves complete in both CTAs
+        else
+          tc_commit(&acc_full[as]);
       }
     }
   } else {
@@ -305,9 +377,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int row_in_tile = q * 32 + lane;
     uint8_t* my_stage = smem + L::EPI_OFFSET + e * EPI_BUF_BYTES;  // 2 x 2 KB
     int j = 0, chunk_ctr = 0;
+    auto release_acc = [&](uint64_t* bar) {  // hand the accumulator back to the (leader's) MMA warp
+      if (PAIR)
+        mbar_arrive_cluster(mapa_rank(smem_u32(bar), 0));
+      else
+        mbar_arrive(bar);
+    };
     for (int w = worker; w < num_work; w += num_workers, ++j) {
       const int wt = w / S, split = w - wt * S;
-      const int m_blk = (wt / g.num_n) * (MC ? 2 : 1) + rank, n_blk = wt % g.num_n;
+      const int m_blk = (wt / g.num_n) * (PAIR ? 2 : 1) + rank, n_blk = wt % g.num_n;
       const int tile = m_blk * g.num_n + n_blk;  // output-tile index (split-K workspace / semaphore slot)
       const int m0 = m_blk * BM, n0 = n_blk * BN;
       const int as = j & 1;
@@ -322,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (m0 >= g.M) {  // padding tile of an odd M-tile pair: nothing to reduce, just recycle the accumulator
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (lane == 0) release_acc(&acc_empty[as]);
           continue;
         }
         float4* wsp = reinterpret_cast<float4*>(g.ws) + ((size_t)(tile * S + split) * (BN / 4)) * BM + row_in_tile;
@@ -339,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);  // accumulator is free again
+        if (lane == 0) release_acc(&acc_empty[as]);  // accumulator is free again
         __threadfence();
         epi_bar_sync();
         if (threadIdx.x == 64) {
@@ -443,17 +521,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) release_acc(&acc_empty[as]);
     }
     if (lane == 0) bulk_wait<0>();
     tc_fence_before();
   }
   __syncthreads();
-  if (MC) cluster_sync_all();  // neither CTA may exit while its peer can still multicast into it
+  if (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal / use it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR)
+      tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -488,73 +569,77 @@ int gemm_init() {
   return get_scratch(&s);
 }
 
-template <int BN, int STAGES, bool MC>
-static int launch_gemm_impl(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
-                            GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES>;
+template <int BN, int STAGES, bool PAIR>
+static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
+                       GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
+  using L = GemmSmem<BN, STAGES, PAIR>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, MC>;
+  auto kern = gemm_tc_kernel<BN, STAGES, PAIR>;
   if (!attr_set) {
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   CUtensorMap b;
-  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, MC ? BN / 2 : BN)) return -1;
-  const int rows_m = MC ? (g.num_m + 1) / 2 : g.num_m;
+  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, PAIR ? BN / 2 : BN)) return -1;
+  const int rows_m = PAIR ? (g.num_m + 1) / 2 : g.num_m;
   const int work = rows_m * g.num_n * g.splits;
-  const int max_workers = MC ? sc.num_sms / 2 : sc.num_sms;
+  const int max_workers = PAIR ? sc.num_sms / 2 : sc.num_sms;
   const int workers = work < max_workers ? work : max_workers;
-  TG_CUDA(launch_kernel(kern, dim3(MC ? 2 * workers : workers), dim3(NUM_THREADS), L::TOTAL, st, MC ? 2 : 1, a1, a2, b, c, g));
+  TG_CUDA(launch_kernel(kern, dim3(PAIR ? 2 * workers : workers), dim3(NUM_THREADS), L::TOTAL, st, PAIR ? 2 : 1, a1, a2, b, c, g));
   TG_COUNT_LAUNCH();
   return 0;
 }
 
-template <int BN, int STAGES>
-static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
-                       GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
-  // Multicast pairs (two M-tiles sharing a weight tile) are opt-in (TG_GEMM_MC=1): measured on B200 they do not
-  // help -- these tiles are bound by per-SM smem ingest (~50 B/clk), which multicast does not reduce.
-  static int use_mc = -1;
-  if (use_mc < 0) {
-    const char* e = getenv("TG_GEMM_MC");
-    use_mc = (e && e[0] == '1') ? 1 : 0;
+// CTA pairs (cta_group::2) are the default whenever a problem has >= 2 M-tiles; TG_GEMM_PAIR=0 forces single-CTA tiles
+// (A/B measurements).
+static bool pair_enabled() {
+  static int use = -1;
+  if (use < 0) {
+    const char* e = getenv("TG_GEMM_PAIR");
+    use = (e && e[0] == '0') ? 0 : 1;
   }
-  if (use_mc && g.num_m >= 2) return launch_gemm_impl<BN, STAGES, true>(a1, a2, Wt, c, g, sc, st);
-  return launch_gemm_impl<BN, STAGES, false>(a1, a2, Wt, c, g, sc, st);
+  return use == 1;
 }
 
-// Tile width / split choice: minimise   waves(work items over the SMs) x (k-blocks per item x per-k-block cost +
-// epilogue).  Measured on B200: a 128 x BN x 64 k-block is bound by the SM's shared-memory ingest (~51 B/clk, i.e.
-// (16 KB + 128*BN B) / 51 cycles) long before the tensor pipe (2*BN cycles), so wider tiles are always cheaper per
-// flop and wave quantisation decides the rest; split-K fills the SMs when M is small and K long.
-static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out) {
+// Tile width / pairing / split choice: minimise   waves(work items over the workers) x (k-blocks per item x
+// per-k-block cost + epilogue).  Measured on B200: a single-CTA 128 x BN x 64 k-block is bound by the SM's shared-memory
+// ingest (~51 B/clk, i.e. (16 KB + 128*BN B) / 51 cycles) long before the tensor pipe (2*BN cycles); a CTA pair
+// (256 x BN per two SMs) stages only 16 KB + 64*BN B per SM for the same 2*BN tensor cycles.  Wider tiles are cheaper
+// per flop and wave quantisation decides the rest; split-K fills the SMs when M is small and K long.
+static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out, int* pair_out) {
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
   const int cands[5] = {256, 192, 160, 128, 64};
   double best_cost = 1e30;
   *bn_out = 64;
   *split_out = 1;
-  for (int i = 0; i < 5; ++i) {
-    const int bn = cands[i];
-    if (N % bn) continue;
-    if (act == 2 && bn % 128) continue;
-    const int tiles = num_m * (N / bn);
-    int s = 1;
-    if (act != 2 && tiles * 2 <= num_sms && nk >= 16) {
-      s = num_sms / tiles;
-      if (s > MAX_SPLIT) s = MAX_SPLIT;
-      if (s > nk / 8) s = nk / 8;
-      if (s < 1) s = 1;
-      while (s > 1 && ((size_t)tiles * s * BM * bn * 4 > SPLITK_WS_BYTES || tiles > SPLITK_MAX_TILES)) --s;
-    }
-    const int waves = (tiles * s + num_sms - 1) / num_sms;
-    const double ingest = (16384.0 + 128.0 * bn) / 51.0;
-    const double per_kb = (2.0 * bn > ingest) ? 2.0 * bn : ingest;
-    const double epi = 1500.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
-    const double cost = waves * (per_kb * ((nk + s - 1) / s) + epi);
-    if (cost < best_cost * 0.999) {
-      best_cost = cost;
-      *bn_out = bn;
-      *split_out = s;
+  *pair_out = 0;
+  for (int pair = (pair_enabled() && num_m >= 2) ? 1 : 0; pair >= 0; --pair) {
+    const int workers = pair ? num_sms / 2 : num_sms;
+    const int rows_m = pair ? (num_m + 1) / 2 : num_m;
+    for (int i = 0; i < 5; ++i) {
+      const int bn = cands[i];
+      if (N % bn) continue;
+      if (act == 2 && bn % 128) continue;
+      const int tiles = rows_m * (N / bn);
+      int s = 1;
+      if (act != 2 && tiles * 2 <= workers && nk >= 16) {
+        s = workers / tiles;
+        if (s > MAX_SPLIT) s = MAX_SPLIT;
+        if (s > nk / 8) s = nk / 8;
+        if (s < 1) s = 1;
+        while (s > 1 && ((size_t)num_m * (N / bn) * s * BM * bn * 4 > SPLITK_WS_BYTES || num_m * (N / bn) > SPLITK_MAX_TILES)) --s;
+      }
+      const int waves = (tiles * s + workers - 1) / workers;
+      const double ingest = (16384.0 + (pair ? 64.0 : 128.0) * bn) / 51.0;
+      const double per_kb = (2.0 * bn > ingest) ? 2.0 * bn : ingest;
+      const double epi = 1500.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
+      const double cost = waves * (per_kb * ((nk + s - 1) / s) + epi);
+      if (cost < best_cost * 0.999) {
+        best_cost = cost;
+        *bn_out = bn;
+        *split_out = s;
+        *pair_out = pair;
+      }
     }
   }
 }
@@ -565,8 +650,8 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   DeviceScratch* sc;
   if (get_scratch(&sc)) return -1;
   const int n_out = g.act == 2 ? g.N / 2 : g.N;
-  int bn, splits;
-  pick_tile(g.M, g.N, g.K, g.act, sc->num_sms, &bn, &splits);
+  int bn, splits, pair;
+  pick_tile(g.M, g.N, g.K, g.act, sc->num_sms, &bn, &splits, &pair);
   CUtensorMap c;  // epilogue chunks: 32 rows x 32 columns (64-byte rows, 64B swizzle)
   if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) return -1;
   g.num_m = (g.M + BM - 1) / BM;
@@ -574,12 +659,21 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   g.splits = splits;
   g.ws = sc->ws;
   g.sem = sc->sem;
+  if (pair) {  // half-width weight stages -> deeper rings
+    switch (bn) {
+      case 256: return launch_gemm<256, 6, true>(a1, a2, Wt, c, g, *sc, st);
+      case 192: return launch_gemm<192, 6, true>(a1, a2, Wt, c, g, *sc, st);
+      case 160: return launch_gemm<160, 7, true>(a1, a2, Wt, c, g, *sc, st);
+      case 128: return launch_gemm<128, 8, true>(a1, a2, Wt, c, g, *sc, st);
+      default: return launch_gemm<64, 8, true>(a1, a2, Wt, c, g, *sc, st);
+    }
+  }
   switch (bn) {
-    case 256: return launch_gemm<256, 4>(a1, a2, Wt, c, g, *sc, st);
-    case 192: return launch_gemm<192, 4>(a1, a2, Wt, c, g, *sc, st);
-    case 160: return launch_gemm<160, 5>(a1, a2, Wt, c, g, *sc, st);
-    case 128: return launch_gemm<128, 6>(a1, a2, Wt, c, g, *sc, st);
-    default: return launch_gemm<64, 8>(a1, a2, Wt, c, g, *sc, st);
+    case 256: return launch_gemm<256, 4, false>(a1, a2, Wt, c, g, *sc, st);
+    case 192: return launch_gemm<192, 4, false>(a1, a2, Wt, c, g, *sc, st);
+    case 160: return launch_gemm<160, 5, false>(a1, a2, Wt, c, g, *sc, st);
+    case 128: return launch_gemm<128, 6, false>(a1, a2, Wt, c, g, *sc, st);
+    default: return launch_gemm<64, 8, false>(a1, a2, Wt, c, g, *sc, st);
   }
 }
 

@@ -15,14 +15,193 @@ namespace tg {
 
 static constexpr int GN_GROUPS = 32;
 static constexpr int GN_MAX_SLABS = 64;
-static constexpr int GN_THREADS = 320;  // >= C/8 for C <= 2560
-static constexpr int GN_VEC = 4;
+static constexpr int GN_THREADS = 320;  // two-pass kernels: >= C/8 for C <= 2560
+static constexpr int GN_FUSED_THREADS = 512;
+static constexpr int GN_FUSED_CLUSTER = 8;
+static constexpr int GN_FUSED_MAX_STAGE = 168 * 1024;  // bytes of one CTA's slab kept on chip
 static constexpr int GN_MAX_BATCH = 256;
 
-// partial[b][slab][g][2] = (sum, sumsq) over the slab's pixels of group g.
-// Thread (r, chunk) owns one 16-byte column chunk (8 channels) and walks rows r, r+R, ... of the slab with four
-// independent 16-byte loads in flight; row-lanes are then combined through shared memory in a fixed order and one
-// thread per group adds its channels in a fixed order: no atomics -> bit-reproducible statistics.
+// tunables (tools/gn_bench.py sweeps them through tg_groupnorm_tune): slabs per image of the statistics kernel (a
+// function of the tensor shape only -- never of the batch -- so an image's statistics are summed in the same order
+// whatever batch it travels in), CTAs per SM of the apply kernel, and whether the single-kernel cluster path may be used
+static int g_gn_stats_slabs = GN_MAX_SLABS, g_gn_apply_per_sm = 8, g_gn_fused = 1;
+void groupnorm_tune(int stats_slabs, int apply_per_sm, int fused) {
+  if (stats_slabs > 0) g_gn_stats_slabs = stats_slabs < GN_MAX_SLABS ? stats_slabs : GN_MAX_SLABS;
+  if (apply_per_sm > 0) g_gn_apply_per_sm = apply_per_sm;
+  if (fused >= 0) g_gn_fused = fused;
+}
+
+__device__ __forceinline__ void gn_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void gn_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ld_dsmem_f32(const float* local, uint32_t rank) {
+  uint32_t a;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void gn_acc8(const uint4& v, float (&s)[8], float (&q)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+    s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+  }
+}
+
+// Thread (rl, chunk) owns one 16-byte column chunk (8 channels) and walks rows r0+rl, r0+rl+R, ... with four
+// independent 16-byte loads in flight.  STAGE: every loaded vector is also parked in shared memory at the thread's own
+// slot (read back by the same thread in the apply pass -> no synchronisation, conflict-free).
+template <bool STAGE>
+__device__ __forceinline__ void gn_accumulate(const __half* __restrict__ src, int ld, int r0, int r1, int R, int rl,
+                                              float (&s)[8], float (&q)[8], uint4* stage, int c8n, int chunk) {
+  int r = r0 + rl;
+  for (; r + 3 * R < r1; r += 4 * R) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      gn_acc8(v[u], s, q);
+      if (STAGE) stage[(size_t)(r + u * R - r0) * c8n + chunk] = v[u];
+    }
+  }
+  for (; r < r1; r += R) {
+    const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld);
+    gn_acc8(v, s, q);
+    if (STAGE) stage[(size_t)(r - r0) * c8n + chunk] = v;
+  }
+}
+
+// CTA-wide reduction of the per-thread channel sums to the 32 groups, in a FIXED order (no atomics -> bit-reproducible):
+// row lanes are folded per channel by all threads, then 64 threads (group, sum|sumsq) add their cpg channels.
+// s_lane: [2][R][C] floats.  Result in s_grp[64] = (sum, sumsq) per group.
+__device__ __forceinline__ void gn_reduce_groups(const float (&s)[8], const float (&q)[8], bool active, int C, int cpg,
+                                                 int R, int rl, int c, float* s_lane, float* s_grp) {
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_lane[rl * C + c + j] = s[j];
+      s_lane[(R + rl) * C + c + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i >= C, ch = i - which * C;
+    float* p = s_lane + (size_t)which * R * C + ch;
+    float a = p[0];
+    for (int k = 1; k < R; ++k) a += p[k * C];
+    p[0] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    const float* p = s_lane + (size_t)which * R * C + g * cpg;
+    float a = 0.f;
+    for (int k = 0; k < cpg; ++k) a += p[k];
+    s_grp[threadIdx.x] = a;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void gn_scale_shift(const float* __restrict__ stat /*[32][2] mean,rstd*/,
+                                               const __half* __restrict__ gamma, const __half* __restrict__ beta, int c,
+                                               int cpg, float (&sa)[8], float (&sb)[8]) {
+  const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + c));
+  const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + c));
+  const __half* hg = reinterpret_cast<const __half*>(&gm);
+  const __half* hb = reinterpret_cast<const __half*>(&bt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c + j) / cpg;
+    const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+    sa[j] = rstd * __half2float(hg[j]);
+    sb[j] = __half2float(hb[j]) - mean * sa[j];
+  }
+}
+
+__device__ __forceinline__ uint4 gn_emit(const uint4& v, const float (&sa)[8], const float (&sb)[8], int silu) {
+  const __half* hv = reinterpret_cast<const __half*>(&v);
+  uint4 o;
+  __half* ho = reinterpret_cast<__half*>(&o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float y = fmaf(__half2float(hv[j]), sa[j], sb[j]);
+    if (silu) y = silu_f(y);
+    ho[j] = __float2half_rn(y);
+  }
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// single-kernel path: one cluster of GN_FUSED_CLUSTER CTAs per image.  Each CTA streams its slab of rows ONCE from
+// global memory into shared memory while accumulating the statistics, the eight CTAs exchange their 32 x (sum, sumsq)
+// through distributed shared memory, and the slab is normalised (+SiLU) straight out of shared memory: one HBM read, one
+// HBM write, one launch.  Used whenever a slab (HW/8 rows x C) fits on chip (all 8x8 / 16x16 tensors and the 640-channel
+// 32x32 ones).  The cluster size is a function of the tensor shape only, so an image's result does not depend on the
+// batch it travels in.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_FUSED_THREADS, 1)
+gn_fused_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
+                __half* __restrict__ out) {
+  grid_dep_launch();
+  grid_dep_wait();
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  __shared__ float s_grp[2 * GN_GROUPS];
+  __shared__ float s_stat[2 * GN_GROUPS];
+  const int b = blockIdx.y, rank = blockIdx.x;  // gridDim.x == cluster size
+  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
+  const int rows_per = HW / GN_FUSED_CLUSTER;
+  const int r0 = rank * rows_per, r1 = r0 + rows_per;
+  const int R = GN_FUSED_THREADS / c8n;
+  uint4* stage = reinterpret_cast<uint4*>(s_raw);
+  float* s_lane = reinterpret_cast<float*>(s_raw + (size_t)rows_per * C * 2);
+  const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  const bool active = rl < R;
+  const int c = chunk * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (active) {
+    const __half* src;
+    int ld;
+    if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
+    src += (size_t)b * HW * ld;
+    gn_accumulate<true>(src, ld, r0, r1, R, rl, s, q, stage, c8n, chunk);
+  }
+  gn_reduce_groups(s, q, active, C, cpg, R, rl, c, s_lane, s_grp);
+  gn_cluster_arrive();
+  gn_cluster_wait();  // every CTA's s_grp is complete and visible
+  if (threadIdx.x < 2 * GN_GROUPS) {
+    float a = 0.f;
+    for (uint32_t k = 0; k < GN_FUSED_CLUSTER; ++k) a += ld_dsmem_f32(&s_grp[threadIdx.x], k);  // fixed order
+    const float other = __shfl_xor_sync(0xffffffffu, a, 1);  // lanes (2g, 2g+1) = (sum, sumsq)
+    const float n = (float)HW * cpg;
+    const float sum = (threadIdx.x & 1) ? other : a, sq = (threadIdx.x & 1) ? a : other;
+    const float mean = sum / n;
+    const float var = fmaxf(sq / n - mean * mean, 0.f);
+    s_stat[threadIdx.x] = (threadIdx.x & 1) ? rsqrtf(var + eps) : mean;
+  }
+  gn_cluster_arrive();  // my remote reads are done (peers may exit once everybody has arrived)
+  __syncthreads();
+  if (active) {
+    float sa[8], sb[8];
+    gn_scale_shift(s_stat, gamma, beta, c, cpg, sa, sb);
+    __half* dst = out + (size_t)b * HW * C + c;
+    for (int r = r0 + rl; r < r1; r += R)
+      *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(stage[(size_t)(r - r0) * c8n + chunk], sa, sb, silu);
+  }
+  gn_cluster_wait();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// two-pass path (tensors too large to park on chip): statistics, then normalise (second read served by L2).
+// partial[b][slab][64] = (sum, sumsq) per group over the slab's pixels; the last slab-CTA of an image to arrive folds
+// the partials in a fixed order into mean / rstd.
+// ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW, int slabs,
                 float* __restrict__ partial, float* __restrict__ stats, int* __restrict__ counters, float eps) {
@@ -33,62 +212,26 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   const int rows_per = (HW + slabs - 1) / slabs;
   const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
   const int R = GN_THREADS / c8n;  // row lanes (>= 1 because c8n <= GN_THREADS)
-  extern __shared__ float s_gn[];  // [R][C] sums, then [R][C] sumsq
-  float* s_sum = s_gn;
-  float* s_sq = s_gn + R * C;
+  extern __shared__ float s_gn[];  // [2][R][C]
+  __shared__ float s_grp[2 * GN_GROUPS];
+  __shared__ int s_last;
   const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
-  if (rl < R) {
-    const int c = chunk * 8;
+  const bool active = rl < R;
+  const int c = chunk * 8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (active) {
     const __half* src;
     int ld;
     if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
     src += (size_t)b * HW * ld;
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    int r = r0 + rl;
-    for (; r + 3 * R < r1; r += 4 * R) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h[j]);
-          s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-          s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-        }
-      }
-    }
-    for (; r < r1; r += R) {
-      const uint4 v = *reinterpret_cast<const uint4*>(src + (size_t)r * ld);
-      const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s_sum[rl * C + c + j] = s[j];
-      s_sq[rl * C + c + j] = q[j];
-    }
+    gn_accumulate<false>(src, ld, r0, r1, R, rl, s, q, nullptr, c8n, chunk);
   }
-  __syncthreads();
-  if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, q = 0.f;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
-      for (int k = 0; k < R; ++k) { s += s_sum[k * C + c]; q += s_sq[k * C + c]; }
-    float* o = partial + (((size_t)b * slabs + slab) * GN_GROUPS + threadIdx.x) * 2;
-    o[0] = s;
-    o[1] = q;
-  }
+  gn_reduce_groups(s, q, active, C, cpg, R, rl, c, s_gn, s_grp);
+  if (threadIdx.x < 2 * GN_GROUPS)
+    partial[((size_t)b * slabs + slab) * 2 * GN_GROUPS + threadIdx.x] = s_grp[threadIdx.x];
   // the last slab-CTA of this image to arrive folds the partials (fixed order) into mean / rstd
-  __shared__ int s_last;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -99,13 +242,22 @@ gn_stats_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // 256 threads: value v = (group, sum|sumsq), four interleaved slab lanes with independent loads in flight, folded
+  // (l0 + l1) + (l2 + l3)
+  if (threadIdx.x < 8 * GN_GROUPS) {
+    const int v = threadIdx.x >> 2, part = threadIdx.x & 3;
+    const float* p = partial + (size_t)b * slabs * 2 * GN_GROUPS + v;
+    float a = 0.f;
+    for (int i = part; i < slabs; i += 4) a += __ldcg(p + (size_t)i * 2 * GN_GROUPS);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    if (part == 0) s_grp[v] = a;
+  }
+  __syncthreads();
   if (threadIdx.x < GN_GROUPS) {
-    float s = 0.f, q = 0.f;
-    const float* p = partial + ((size_t)b * slabs * GN_GROUPS + threadIdx.x) * 2;
-    for (int i = 0; i < slabs; ++i, p += GN_GROUPS * 2) { s += __ldcg(p); q += __ldcg(p + 1); }
     const float n = (float)HW * cpg;
-    const float mean = s / n;
-    const float var = fmaxf(q / n - mean * mean, 0.f);
+    const float mean = s_grp[2 * threadIdx.x] / n;
+    const float var = fmaxf(s_grp[2 * threadIdx.x + 1] / n - mean * mean, 0.f);
     stats[((size_t)b * GN_GROUPS + threadIdx.x) * 2] = mean;
     stats[((size_t)b * GN_GROUPS + threadIdx.x) * 2 + 1] = rsqrtf(var + eps);
   }
@@ -126,19 +278,7 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   if (rl >= R) return;
   const int c = chunk * 8;
   float sa[8], sb[8];
-  {
-    const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + c));
-    const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + c));
-    const __half* hg = reinterpret_cast<const __half*>(&gm);
-    const __half* hb = reinterpret_cast<const __half*>(&bt);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c + j) / cpg;
-      const float mean = stats[((size_t)b * GN_GROUPS + g) * 2], rstd = stats[((size_t)b * GN_GROUPS + g) * 2 + 1];
-      sa[j] = rstd * __half2float(hg[j]);
-      sb[j] = __half2float(hb[j]) - mean * sa[j];
-    }
-  }
+  gn_scale_shift(stats + (size_t)b * GN_GROUPS * 2, gamma, beta, c, cpg, sa, sb);
   const __half* src;
   int ld;
   if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
@@ -146,54 +286,57 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
   __half* dst = out + (size_t)b * HW * C + c;
   const int rows_per = (HW + slabs - 1) / slabs;
   const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
-  auto emit = [&](const uint4& v, int r) {
-    const __half* hv = reinterpret_cast<const __half*>(&v);
-    uint4 o;
-    __half* ho = reinterpret_cast<__half*>(&o);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = fmaf(__half2float(hv[j]), sa[j], sb[j]);
-      if (silu) y = silu_f(y);
-      ho[j] = __float2half_rn(y);
-    }
-    *reinterpret_cast<uint4*>(dst + (size_t)r * C) = o;
-  };
   int r = r0 + rl;
   for (; r + 3 * R < r1; r += 4 * R) {
     uint4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(v[u], r + u * R);
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(dst + (size_t)(r + u * R) * C) = gn_emit(v[u], sa, sb, silu);
   }
-  for (; r < r1; r += R) emit(*reinterpret_cast<const uint4*>(src + (size_t)r * ld), r);
+  for (; r < r1; r += R)
+    *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(*reinterpret_cast<const uint4*>(src + (size_t)r * ld), sa, sb, silu);
 }
 
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st) {
   const int C = C1 + C2;
   TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN_THREADS, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
-  TG_CHECK(workspace != nullptr, "groupnorm: zero-initialised workspace (16640 + B*4096 floats) required");
-  // enough slabs for >= ~4 CTAs per SM, at least 8 rows per row-lane pass
-  int slabs = (4 * 148 + B - 1) / B;
-  const int R = GN_THREADS / (C / 8);
-  slabs = max(1, min(min(slabs, GN_MAX_SLABS), HW / max(1, 2 * R)));
-  const size_t smem = (size_t)2 * R * C * sizeof(float);
+  TG_CHECK(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
   static bool attr = false;
   if (!attr) {
     TG_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TG_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr = true;
   }
+  // ---- single-kernel cluster path ----
+  if (g_gn_fused && HW % GN_FUSED_CLUSTER == 0) {
+    const int rows_per = HW / GN_FUSED_CLUSTER;
+    const size_t stage = (size_t)rows_per * C * 2;
+    const int Rf = GN_FUSED_THREADS / (C / 8);
+    const size_t smem = stage + (size_t)2 * Rf * C * sizeof(float);
+    if (stage <= GN_FUSED_MAX_STAGE && smem <= 222 * 1024) {
+      TG_CUDA(launch_kernel(gn_fused_kernel, dim3(GN_FUSED_CLUSTER, B), dim3(GN_FUSED_THREADS), smem, st,
+                            GN_FUSED_CLUSTER, x1, C1, x2, C2, HW, gamma, beta, eps, silu, out));
+      TG_COUNT_LAUNCH();
+      TG_LAUNCH_CHECK();
+      return 0;
+    }
+  }
+  // ---- two-pass path ----
+  TG_CHECK(workspace != nullptr, "groupnorm: zero-initialised workspace (16640 + B*4096 floats) required");
+  const int R = GN_THREADS / (C / 8);
+  const int slabs = max(1, min(g_gn_stats_slabs, HW / max(1, 2 * R)));
+  const size_t smem = (size_t)2 * R * C * sizeof(float);
   TG_CHECK(smem <= 64 * 1024, "groupnorm: smem %zu too large", smem);
   // workspace layout (fixed offsets, independent of B): [256 arrival counters][256 x 32 x (mean, rstd)][partials]
-  TG_CHECK(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
   int* counters = reinterpret_cast<int*>(workspace);
   float* stats = workspace + GN_MAX_BATCH;
   float* partial = stats + (size_t)GN_MAX_BATCH * GN_GROUPS * 2;
   TG_CUDA(launch_kernel(gn_stats_kernel, dim3(slabs, B), dim3(GN_THREADS), smem, st, 1, x1, C1, x2, C2, HW, slabs, partial, stats, counters, eps));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
-  int aslabs = (8 * 148 + B - 1) / B;  // ~8 CTAs per SM in flight, >= 4 rows per row-lane
+  int aslabs = (g_gn_apply_per_sm * 148 + B - 1) / B;
   aslabs = max(1, min(aslabs, HW / max(1, 4 * R)));
   TG_CUDA(launch_kernel(gn_apply_kernel, dim3(aslabs, B), dim3(GN_THREADS), 0, st, 1, x1, C1, x2, C2, HW, aslabs, stats, gamma, beta, silu, out));
   TG_COUNT_LAUNCH();

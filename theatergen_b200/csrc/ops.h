@@ -31,6 +31,8 @@ int gemm_init();
 // workspace: >= B*64*32*2 floats.
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st);
+// launch-geometry knobs of groupnorm_nhwc (<= 0 / < 0 keep the current value); used by tools/gn_bench.py
+void groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused);
 int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* beta, float eps, __half* out,
                    int ldo, int M, int C, cudaStream_t st);
 

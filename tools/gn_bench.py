@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""GroupNorm(+SiLU) timing per SD-1.5 tensor shape: single-kernel cluster path vs two-pass kernels, with the launch
+geometry knobs of tg_groupnorm_tune swept (run on the GPU box).  Each measurement replays a CUDA graph of 20 calls
+that alternate between 4 distinct input tensors so that the inputs are not L2-resident from the previous call."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from theatergen_b200 import _lib, ops
+
+
+def graph_time(fn, reps=5):
+    fn(); fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    shapes = [(4096, 320, 0), (4096, 640, 320), (4096, 320, 320), (1024, 640, 0), (1024, 1280, 640), (1024, 640, 320),
+              (256, 1280, 0), (256, 1280, 1280), (64, 1280, 0), (64, 1280, 1280)]
+    print(f"B={B}; us per GroupNorm+SiLU call (graph of 20 calls over 4 rotating inputs)")
+    print(f"{'HW':>5s} {'C1':>5s} {'C2':>5s} {'MB':>7s} | {'fused':>7s} | two-pass (stats_slabs, apply_ctas_per_sm) ...")
+    for HW, C1, C2 in shapes:
+        C = C1 + C2
+        xs1 = [torch.randn(B, HW, C1, device="cuda").half() for _ in range(4)]
+        xs2 = [torch.randn(B, HW, C2, device="cuda").half() if C2 else None for _ in range(4)]
+        gamma, beta = torch.ones(C, device="cuda").half(), torch.zeros(C, device="cuda").half()
+        out = torch.empty(B, HW, C, device="cuda", dtype=torch.float16)
+
+        def run():
+            for i in range(20):
+                ops.groupnorm(xs1[i % 4], gamma, beta, 1e-5, x2=xs2[i % 4], silu=True, out=out)
+
+        row = []
+        _lib.lib().tg_groupnorm_tune(64, 8, 1)
+        row.append(f"{graph_time(run) / 20 * 1e3:7.1f}")
+        for slabs in (16, 32, 64):
+            for per_sm in (4, 8, 16):
+                _lib.lib().tg_groupnorm_tune(slabs, per_sm, 0)
+                row.append(f"({slabs},{per_sm}) {graph_time(run) / 20 * 1e3:6.1f}")
+        _lib.lib().tg_groupnorm_tune(64, 8, 1)
+        mb = B * HW * C * 2 / 1e6
+        print(f"{HW:5d} {C1:5d} {C2:5d} {mb:7.1f} | {row[0]} | " + "  ".join(row[1:]))
+
+
+if __name__ == "__main__":
+    main()
