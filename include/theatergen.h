@@ -49,12 +49,14 @@ int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, co
             int K, const tg_half* bias, const tg_half* rowbias, int rows_per_image, int rowbias_ld,
             const tg_half* residual, int ldr, int act, float out_scale, tg_half* out, int ldc, void* stream);
 
-/* out[B*H*W, Cout] = conv3x3(pad=1, stride=1)(X[B,H,W,Cin]) + bias + rowbias[b] (+ residual) * out_scale
- * implicit GEMM on tcgen05; padding comes from TMA out-of-bounds zero fill.  Wt = [Cout,3,3,Cin].
+/* out[B*H*W, Cout] = (act(conv3x3(pad=1, stride=1)(X[B,H,W,Cin]) + bias + rowbias[b]) + residual) * out_scale
+ * implicit GEMM on tcgen05; padding comes from TMA out-of-bounds zero fill.  Wt = [Cout,3,3,Cin]; Cin, Cout multiples
+ * of 64; W divides 128 or is a multiple of 128.  act: 0 none, 1 SiLU.
  * Replaces the 3x3 convolutions of diffusers ResnetBlock2D / Upsample2D (call sites
- * ip_adapter/unet_2d_blocks.py:668,709,1093,1192,2239,2328,2184,2251,2298,2332). */
+ * ip_adapter/unet_2d_blocks.py:668,709,1093,1192,2239,2328,2184,2251,2298,2332) and of the stage-2 ControlNet's
+ * conditioning embedder (stock diffusers ControlNetModel built at generate.py:91, called models/pipelines.py:770-778). */
 int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt, int Cout, const tg_half* bias,
-               const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, float out_scale,
+               const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, int act, float out_scale,
                tg_half* out, int ldc, void* stream);
 
 /* out = [SiLU](GroupNorm32([x1|x2])) for channels-last x1 [B,HW,C1], x2 [B,HW,C2] (x2 NULL when C2 == 0).
@@ -65,6 +67,11 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
  * (ip_adapter/unet_2d_condition.py:1117-1119). */
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream);
+
+/* Measurement hook (no reference counterpart): with a non-NULL device buffer of >= 8*grid int64, every tg_gemm /
+ * tg_conv3x3 CTA records {main-loop cycles, producer wait, MMA wait on data, MMA wait on accumulator, epilogue wait,
+ * k-blocks, tiles} so a run can tell which role of the pipeline the others wait for.  NULL switches it off. */
+int tg_gemm_set_prof(void* dev_buf);
 
 /* Launch-geometry knobs of tg_groupnorm for measurements (values <= 0 keep the current setting; fused: 1 allows the
  * single-kernel cluster path for tensors whose per-image slab fits on chip, 0 forces the two-pass kernels, <0 keeps).
@@ -106,8 +113,9 @@ int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg
  * diffusers Upsample2D / Downsample2D) */
 int tg_upsample2x(const tg_half* x, int B, int H, int W, int C, tg_half* y, void* stream);
 int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, void* stream);
-int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_half* y_nhwc, int B, int H, int W,
-               int Cout, void* stream);
+/* conv_in: NCHW [B,Cin,H,W] (Cin = 4 latents, or 3 for the ControlNet hint image) -> NHWC [B,H,W,Cout], optional SiLU */
+int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_half* y_nhwc, int B, int Cin, int H,
+               int W, int Cout, int silu, void* stream);
 int tg_conv_out(const tg_half* x_nhwc, const tg_half* w, const tg_half* bias, tg_half* y_nchw, int B, int H,
                 int W, int C, void* stream);
 int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream);

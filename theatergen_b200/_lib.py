@@ -19,8 +19,9 @@ _SIGS = {
     "tg_launch_count": (C.c_ulonglong, []),
     "tg_init": (ci, []),
     "tg_gemm": (ci, [vp, ci, ci, vp, ci, vp, ci, ci, ci, vp, vp, ci, ci, vp, ci, ci, cf, vp, ci, vp]),
-    "tg_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, cf, vp, ci, vp]),
+    "tg_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, ci, cf, vp, ci, vp]),
     "tg_groupnorm": (ci, [vp, ci, vp, ci, ci, ci, vp, vp, cf, ci, vp, vp, vp]),
+    "tg_gemm_set_prof": (ci, [vp]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),
     "tg_attention": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, cf, vp]),
@@ -28,7 +29,7 @@ _SIGS = {
     "tg_attention_cross_ip": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_upsample2x": (ci, [vp, ci, ci, ci, ci, vp, vp]),
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, vp]),
-    "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_conv_out": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "tg_timestep_embedding": (ci, [vp, vp, ci, ci, vp]),
     "tg_add_inplace": (ci, [vp, vp, C.c_longlong, vp]),

@@ -26,12 +26,13 @@ int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, co
 }
 
 int tg_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* Wt, int Cout, const tg_half* bias,
-               const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, float out_scale,
+               const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, int act, float out_scale,
                tg_half* out, int ldc, void* stream) {
   TG_CHECK(X && Wt && out, "tg_conv3x3: null pointer");
+  TG_CHECK(act == 0 || act == 1 || act == 3, "tg_conv3x3: act must be none / silu / gelu");
   tg::EpilogueSpec e;
   e.bias = H(bias); e.rowbias = H(rowbias); e.rows_per_image = Hh * W; e.rowbias_ld = rowbias_ld;
-  e.residual = H(residual); e.ldr = ldr; e.act = 0; e.out_scale = out_scale;
+  e.residual = H(residual); e.ldr = ldr; e.act = act; e.out_scale = out_scale;
   return tg::conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, e, HM(out), ldc, ST(stream));
 }
 
@@ -40,6 +41,11 @@ int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, in
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream) {
   TG_CHECK(x1 && gamma && beta && out && (C2 == 0 || x2), "tg_groupnorm: null pointer");
   return tg::groupnorm_nhwc(H(x1), C1, H(x2), C2, B, HW, H(gamma), H(beta), eps, silu, HM(out), workspace, ST(stream));
+}
+
+int tg_gemm_set_prof(void* dev_buf) {
+  tg::gemm_set_prof(static_cast<long long*>(dev_buf));
+  return 0;
 }
 
 int tg_groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused) {
@@ -82,10 +88,10 @@ int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, void
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), ST(stream));
 }
-int tg_conv_in(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int Cout,
-               void* stream) {
+int tg_conv_in(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Cin, int Hh, int W,
+               int Cout, int silu, void* stream) {
   TG_CHECK(x && w && bias && y, "tg_conv_in: null pointer");
-  return tg::conv_in_nchw_to_nhwc(H(x), H(w), H(bias), HM(y), B, Hh, W, Cout, ST(stream));
+  return tg::conv_in_nchw_to_nhwc(H(x), H(w), H(bias), HM(y), B, Cin, Hh, W, Cout, silu, ST(stream));
 }
 int tg_conv_out(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int C,
                 void* stream) {

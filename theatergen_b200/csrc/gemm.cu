@@ -37,6 +37,7 @@ namespace tg {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
+static constexpr int KPS = 2;                    // k-blocks (64-wide, one SWIZZLE_128B tile each) per pipeline stage
 static constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, alternating column chunks
 static constexpr int EPI_BUF_BYTES = 2 * 32 * 64;  // per warp: two staging buffers of 32 rows x 32 fp16
 static constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
@@ -58,13 +59,14 @@ struct GemmArgs {
   int num_m, num_n, splits;
   float* ws;   // split-K partials: [tile][split][BN/4][128][4] fp32
   int* sem;    // split-K arrival counters, one per tile (self-resetting)
+  long long* prof;  // measurement only (tg_gemm_set_prof): per CTA {total, producer wait, MMA wait full, MMA wait acc, epilogue wait} cycles
 };
 
 template <int BN, int STAGES, bool PAIR>
 struct GemmSmem {
-  static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // a CTA of a pair stages half of the weight tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int A_BYTES = BM * BK * 2;                    // one k-block of A
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // one k-block of B; a CTA of a pair stages half of the weight tile
+  static constexpr int STAGE_BYTES = KPS * (A_BYTES + B_BYTES);  // [A kb0 | A kb1 | B kb0 | B kb1]
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_BUF_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 32 + 1024;  // + alignment slack
@@ -91,6 +93,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMa
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
       "[%2];" ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
@@ -273,89 +283,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;  // k-iteration counter across work items (ring position)
+      long long p_wait = 0;
       const int hw = g.H * g.W;
       const int cblk = g.mode == 1 ? g.Cin / BK : 1;
       for (int w = worker; w < num_work; w += num_workers) {
         const int wt = w / S, split = w - wt * S;
         const int m0 = ((wt / g.num_n) * (PAIR ? 2 : 1) + rank) * BM, n0 = (wt % g.num_n) * BN;
         const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
-        int conv_b0 = 0, conv_y0 = 0;
+        int conv_b0 = 0, conv_y0 = 0, conv_x0 = 0;
         if (g.mode == 1) {
           conv_b0 = m0 / hw;
           conv_y0 = (m0 % hw) / g.W;
+          conv_x0 = m0 % g.W;  // non-zero only for rows wider than a tile (W > 128: a tile is a 128-pixel row segment)
         }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        // One stage = KPS consecutive k-blocks: the loads of a stage are issued back to back after ONE wait.  Measured on
+        // B200 (tools/probes): a group of TMA loads issued after a barrier wait costs ~570 cycles + ~70 per extra load,
+        // whatever its size, and groups do not overlap each other -- so a stage must carry as much MMA work as possible.
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (g.prof) {
+            const long long t0 = clock64();
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            p_wait += clock64() - t0;
+          } else {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+          }
+          const int nkb = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
           uint8_t* sa = smem + s * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
+          uint8_t* sb = sa + KPS * L::A_BYTES;
+          // the weight box always brings KPS chunks (the one past K is zero-filled by the TMA unit and never multiplied)
+          const uint32_t bytes = nkb * L::A_BYTES + KPS * L::B_BYTES;
+          uint32_t fb = 0;
           if (PAIR) {
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
-            const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
-            if (g.mode == 0) {
-              const int k0 = kb * BK;
-              if (k0 < g.K1)
-                tma_load_2d_2sm(sa, &tmA1, fb, k0, m0);
-              else
-                tma_load_2d_2sm(sa, &tmA2, fb, k0 - g.K1, m0);
-            } else {
-              const int tap = kb / cblk;
-              const int c0 = (kb - tap * cblk) * BK;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              tma_load_4d_2sm(sa, &tmA1, fb, c0, kx - 1, conv_y0 + ky - 1, conv_b0);
-            }
-            tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0 + rank * (BN / 2));  // my half of the weight tile
-            continue;
-          }
-          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          if (g.mode == 0) {
-            const int k0 = kb * BK;
-            if (k0 < g.K1)
-              tma_load_2d(sa, &tmA1, &full_bar[s], k0, m0);
-            else
-              tma_load_2d(sa, &tmA2, &full_bar[s], k0 - g.K1, m0);
+            fb = mapa_rank(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
           } else {
-            const int tap = kb / cblk;
-            const int c0 = (kb - tap * cblk) * BK;
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(sa, &tmA1, &full_bar[s], c0, kx - 1, conv_y0 + ky - 1, conv_b0);
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
+          for (int j = 0; j < nkb; ++j) {
+            uint8_t* dst = sa + j * L::A_BYTES;
+            if (g.mode == 0) {
+              const int k0 = (kb + j) * BK;
+              const CUtensorMap* tm = k0 < g.K1 ? &tmA1 : &tmA2;
+              const int kc = k0 < g.K1 ? k0 : k0 - g.K1;
+              if (PAIR) tma_load_2d_2sm(dst, tm, fb, kc, m0); else tma_load_2d(dst, tm, &full_bar[s], kc, m0);
+            } else {
+              const int tap = (kb + j) / cblk;
+              const int c0 = (kb + j - tap * cblk) * BK;
+              const int ky = tap / 3, kx = tap - ky * 3;
+              if (PAIR) tma_load_4d_2sm(dst, &tmA1, fb, c0, conv_x0 + kx - 1, conv_y0 + ky - 1, conv_b0);
+              else tma_load_4d(dst, &tmA1, &full_bar[s], c0, conv_x0 + kx - 1, conv_y0 + ky - 1, conv_b0);
+            }
+          }
+          if (PAIR) tma_load_3d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb);  // my half of the weight tile
+          else tma_load_3d(sb, &tmB, &full_bar[s], 0, n0, kb);
         }
       }
+      if (g.prof) g.prof[blockIdx.x * 8 + 1] = p_wait;
     }
   } else if (warp == 1) {
     // ===== MMA issuer (single thread) =====
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN);
       int it = 0, j = 0;
+      long long m_wait_full = 0, m_wait_acc = 0;
+      const long long m_t0 = clock64();
       for (int w = worker; w < num_work; w += num_workers, ++j) {
         const int wt = w / S, split = w - wt * S;
         const int kb0 = (nk * split) / S, kb1 = (nk * (split + 1)) / S;
         const int as = j & 1;
-        mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        {
+          const long long t0 = g.prof ? clock64() : 0;
+          mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+          if (g.prof) m_wait_acc += clock64() - t0;
+        }
         tc_fence_after();
         const uint32_t d_addr = tmem_base + as * ACC_STRIDE;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (g.prof) {
+            const long long t0 = clock64();
+            mbar_wait(&full_bar[s], ph);
+            m_wait_full += clock64() - t0;
+          } else {
+            mbar_wait(&full_bar[s], ph);
+          }
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+          const int nkb = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
+          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + KPS * L::A_BYTES;
+          for (int j = 0; j < nkb; ++j) {
+            const uint32_t a_addr = a_base + j * L::A_BYTES, b_addr = b_base + j * L::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
-            if (PAIR)
-              umma_f16_ss_2sm(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else
-              umma_f16_ss(d_addr, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
+              const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
+              const uint32_t acc = (kb + j > kb0 || k > 0) ? 1u : 0u;
+              if (PAIR)
+                umma_f16_ss_2sm(d_addr, da, db, idesc, acc);
+              else
+                umma_f16_ss(d_addr, da, db, idesc, acc);
+            }
           }
           if (PAIR)
-            tc_commit_2sm(&empty_bar[s], 0x3);  // frees the slot in both CTAs when these MMAs retire
+            tc_commit_2sm(&empty_bar[s], 0x3);  // frees the stage in both CTAs when these MMAs retire
           else
             tc_commit(&empty_bar[s]);
         }
@@ -363,6 +397,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           tc_commit_2sm(&acc_full[as], 0x3);  // accumulator halves complete in both CTAs
         else
           tc_commit(&acc_full[as]);
+      }
+      if (g.prof) {
+        g.prof[blockIdx.x * 8 + 0] = clock64() - m_t0;
+        g.prof[blockIdx.x * 8 + 2] = m_wait_full;
+        g.prof[blockIdx.x * 8 + 3] = m_wait_acc;
+        g.prof[blockIdx.x * 8 + 5] = it;
+        g.prof[blockIdx.x * 8 + 6] = j;
       }
     }
   } else {
@@ -377,6 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int row_in_tile = q * 32 + lane;
     uint8_t* my_stage = smem + L::EPI_OFFSET + e * EPI_BUF_BYTES;  // 2 x 2 KB
     int j = 0, chunk_ctr = 0;
+    long long e_wait = 0;
     auto release_acc = [&](uint64_t* bar) {  // hand the accumulator back to the (leader's) MMA warp
       if (PAIR)
         mbar_arrive_cluster(mapa_rank(smem_u32(bar), 0));
@@ -465,7 +507,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       const int c_first = half * step;
       uint4 res_next[4];
       if (c_first < BN) load_residual(g, res_next, m, g.act == 2 ? (n0 + c_first) >> 1 : n0 + c_first, row_ok);
-      mbar_wait(&acc_full[as], (j >> 1) & 1);
+      if (g.prof && e == 0 && lane == 0) {
+        const long long t0 = clock64();
+        mbar_wait(&acc_full[as], (j >> 1) & 1);
+        e_wait += clock64() - t0;
+      } else {
+        mbar_wait(&acc_full[as], (j >> 1) & 1);
+      }
       tc_fence_after();
 #pragma unroll 1
       for (int c = c_first; c < BN; c += 2 * step, ++chunk_ctr) {
@@ -524,6 +572,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       if (lane == 0) release_acc(&acc_empty[as]);
     }
     if (lane == 0) bulk_wait<0>();
+    if (g.prof && e == 0 && lane == 0) g.prof[blockIdx.x * 8 + 4] = e_wait;
     tc_fence_before();
   }
   __syncthreads();
@@ -564,6 +613,9 @@ static int get_scratch(DeviceScratch** out) {
   return 0;
 }
 
+static long long* g_prof = nullptr;
+void gemm_set_prof(long long* dev_buf) { g_prof = dev_buf; }
+
 int gemm_init() {
   DeviceScratch* s;
   return get_scratch(&s);
@@ -580,7 +632,7 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __hal
     attr_set = true;
   }
   CUtensorMap b;
-  if (make_tmap_2d(&b, Wt, g.N, g.K, g.K, PAIR ? BN / 2 : BN)) return -1;
+  if (make_tmap_kchunks(&b, Wt, g.N, g.K, PAIR ? BN / 2 : BN, KPS)) return -1;
   const int rows_m = PAIR ? (g.num_m + 1) / 2 : g.num_m;
   const int work = rows_m * g.num_n * g.splits;
   const int max_workers = PAIR ? sc.num_sms / 2 : sc.num_sms;
@@ -601,11 +653,13 @@ static bool pair_enabled() {
   return use == 1;
 }
 
-// Tile width / pairing / split choice: minimise   waves(work items over the workers) x (k-blocks per item x
-// per-k-block cost + epilogue).  Measured on B200: a single-CTA 128 x BN x 64 k-block is bound by the SM's shared-memory
-// ingest (~51 B/clk, i.e. (16 KB + 128*BN B) / 51 cycles) long before the tensor pipe (2*BN cycles); a CTA pair
-// (256 x BN per two SMs) stages only 16 KB + 64*BN B per SM for the same 2*BN tensor cycles.  Wider tiles are cheaper
-// per flop and wave quantisation decides the rest; split-K fills the SMs when M is small and K long.
+// Tile width / pairing / split choice: minimise   waves(work items over the workers) x (stages per item x per-stage
+// cost + epilogue).  Per-stage cost model, measured on B200 with tools/probes (umma_probe, tma_probe3/5, gemm_roles):
+//   * tensor pipe: a 128(x2) x BN x 16 MMA takes max(88, BN/2) cycles -> KPS*4 of them per stage;
+//   * TMA: the loads issued after one barrier wait cost ~570 cycles + ~70 per extra instruction whatever their size, and
+//     such groups do not overlap; a stage also cannot beat ~74 B/clk of per-SM TMA bandwidth;
+//   whichever is larger.  Wider tiles are cheaper per flop, pairs halve the weight bytes per SM, wave quantisation decides
+//   the rest; split-K fills the SMs when M is small and K long.
 static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out, int* pair_out) {
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
   const int cands[5] = {256, 192, 160, 128, 64};
@@ -613,7 +667,9 @@ static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, in
   *bn_out = 64;
   *split_out = 1;
   *pair_out = 0;
-  for (int pair = (pair_enabled() && num_m >= 2) ? 1 : 0; pair >= 0; --pair) {
+  // short-K problems (K < 640: the 320-channel linears) are paced by the epilogue, where a pair only adds a cross-CTA
+  // hand-off per tile (measured: 574 vs 688 TFLOP/s on the 64x64 qkv projection)
+  for (int pair = (pair_enabled() && num_m >= 2 && nk >= 10) ? 1 : 0; pair >= 0; --pair) {
     const int workers = pair ? num_sms / 2 : num_sms;
     const int rows_m = pair ? (num_m + 1) / 2 : num_m;
     for (int i = 0; i < 5; ++i) {
@@ -630,10 +686,14 @@ static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, in
         while (s > 1 && ((size_t)num_m * (N / bn) * s * BM * bn * 4 > SPLITK_WS_BYTES || num_m * (N / bn) > SPLITK_MAX_TILES)) --s;
       }
       const int waves = (tiles * s + workers - 1) / workers;
-      const double ingest = (16384.0 + (pair ? 64.0 : 128.0) * bn) / 51.0;
-      const double per_kb = (2.0 * bn > ingest) ? 2.0 * bn : ingest;
+      const double mma = KPS * 4.0 * (bn / 2.0 > 88.0 ? bn / 2.0 : 88.0);
+      const double stage_bytes = KPS * (16384.0 + (pair ? 64.0 : 128.0) * bn);
+      double tma = 570.0 + 70.0 * KPS;  // KPS A loads + 1 weight load
+      if (stage_bytes / 74.0 > tma) tma = stage_bytes / 74.0;
+      const double per_stage = mma > tma ? mma : tma;
+      const int kb_per_item = (nk + s - 1) / s;
       const double epi = 1500.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
-      const double cost = waves * (per_kb * ((nk + s - 1) / s) + epi);
+      const double cost = waves * (per_stage * ((kb_per_item + KPS - 1) / KPS) + epi);
       if (cost < best_cost * 0.999) {
         best_cost = cost;
         *bn_out = bn;
@@ -659,21 +719,23 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   g.splits = splits;
   g.ws = sc->ws;
   g.sem = sc->sem;
-  if (pair) {  // half-width weight stages -> deeper rings
+  g.prof = g_prof;
+  // stages of KPS k-blocks; a CTA of a pair stages half of the weight tile -> deeper rings in the same shared memory
+  if (pair) {
     switch (bn) {
-      case 256: return launch_gemm<256, 6, true>(a1, a2, Wt, c, g, *sc, st);
-      case 192: return launch_gemm<192, 6, true>(a1, a2, Wt, c, g, *sc, st);
-      case 160: return launch_gemm<160, 7, true>(a1, a2, Wt, c, g, *sc, st);
-      case 128: return launch_gemm<128, 8, true>(a1, a2, Wt, c, g, *sc, st);
-      default: return launch_gemm<64, 8, true>(a1, a2, Wt, c, g, *sc, st);
+      case 256: return launch_gemm<256, 3, true>(a1, a2, Wt, c, g, *sc, st);   // 64 KB stages
+      case 192: return launch_gemm<192, 3, true>(a1, a2, Wt, c, g, *sc, st);   // 56 KB
+      case 160: return launch_gemm<160, 3, true>(a1, a2, Wt, c, g, *sc, st);   // 52 KB
+      case 128: return launch_gemm<128, 4, true>(a1, a2, Wt, c, g, *sc, st);   // 48 KB
+      default: return launch_gemm<64, 4, true>(a1, a2, Wt, c, g, *sc, st);     // 40 KB
     }
   }
   switch (bn) {
-    case 256: return launch_gemm<256, 4, false>(a1, a2, Wt, c, g, *sc, st);
-    case 192: return launch_gemm<192, 4, false>(a1, a2, Wt, c, g, *sc, st);
-    case 160: return launch_gemm<160, 5, false>(a1, a2, Wt, c, g, *sc, st);
-    case 128: return launch_gemm<128, 6, false>(a1, a2, Wt, c, g, *sc, st);
-    default: return launch_gemm<64, 8, false>(a1, a2, Wt, c, g, *sc, st);
+    case 256: return launch_gemm<256, 2, false>(a1, a2, Wt, c, g, *sc, st);    // 96 KB stages
+    case 192: return launch_gemm<192, 2, false>(a1, a2, Wt, c, g, *sc, st);    // 80 KB
+    case 160: return launch_gemm<160, 2, false>(a1, a2, Wt, c, g, *sc, st);    // 72 KB
+    case 128: return launch_gemm<128, 3, false>(a1, a2, Wt, c, g, *sc, st);    // 64 KB
+    default: return launch_gemm<64, 4, false>(a1, a2, Wt, c, g, *sc, st);      // 48 KB
   }
 }
 
@@ -709,20 +771,21 @@ int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, 
 int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, const EpilogueSpec& e,
                  __half* out, int ldc, cudaStream_t st) {
   TG_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3: Cin/Cout must be multiples of 64 (got %d/%d)", Cin, Cout);
-  TG_CHECK(W <= 128 && 128 % W == 0, "conv3x3: W must divide 128 (got %d)", W);
-  int box_h = 128 / W, box_b = 1;
+  TG_CHECK((W <= 128 && 128 % W == 0) || W % 128 == 0, "conv3x3: W must divide 128 or be a multiple of it (got %d)", W);
+  const int box_w = W < 128 ? W : 128;
+  int box_h = 128 / box_w, box_b = 1;
   if (box_h > H) {
     box_b = box_h / H;
     box_h = H;
   }
-  TG_CHECK(H % box_h == 0 && B % box_b == 0 && box_b * box_h * W == 128, "conv3x3: tile %dx%dx%d does not cover 128",
-           box_b, box_h, W);
+  TG_CHECK(H % box_h == 0 && B % box_b == 0 && box_b * box_h * box_w == 128, "conv3x3: tile %dx%dx%d does not cover 128",
+           box_b, box_h, box_w);
   GemmArgs g{};
   g.M = B * H * W; g.N = Cout; g.K = 9 * Cin; g.K1 = g.K; g.mode = 1;
   g.H = H; g.W = W; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
   fill_args(g, e);
   CUtensorMap a1;
-  if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, W)) return -1;
+  if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, box_w)) return -1;
   return dispatch(a1, a1, g, Wt, out, ldc, st);
 }
 

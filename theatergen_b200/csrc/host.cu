@@ -65,6 +65,23 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+int make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows, uint32_t kc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && K % 64 == 0, "tmap kchunks: alignment (base=%p K=%llu)", base,
+           (unsigned long long)K);
+  cuuint64_t dims[3] = {64, rows, K / 64};
+  cuuint64_t strides[2] = {K * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, kc};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(kchunks rows=%llu K=%llu box=%ux%u) -> %d", (unsigned long long)rows,
+           (unsigned long long)K, box_rows, kc, (int)r);
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
                    uint32_t bh, uint32_t bw) {
   EncodeTiledFn enc = get_encode();

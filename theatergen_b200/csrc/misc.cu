@@ -77,7 +77,7 @@ int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaS
 template <int CIN, int PIX>
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
-               __half* __restrict__ y, int H, int W, int Cout) {
+               __half* __restrict__ y, int H, int W, int Cout, int silu) {
   grid_dep_launch();
   grid_dep_wait();
   extern __shared__ float sm_ci[];
@@ -103,13 +103,15 @@ conv_in_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const
     float acc = __half2float(bias[co]);
 #pragma unroll
     for (int k = 0; k < CIN * 9; ++k) acc += sp[pp * CIN * 9 + k] * sw[k * Cout + co];
+    if (silu) acc = silu_f(acc);
     y[((size_t)b * HW + p0 + pp) * Cout + co] = __float2half_rn(acc);
   }
 }
 
-int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W,
-                         int Cout, cudaStream_t st) {
-  constexpr int CIN = 4, PIX = 32;
+template <int CIN>
+static int conv_in_launch(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int Cout,
+                          int silu, cudaStream_t st) {
+  constexpr int PIX = 32;
   const size_t smem = (size_t)(CIN * 9 * Cout + PIX * CIN * 9) * sizeof(float);
   auto kern = conv_in_kernel<CIN, PIX>;
   static bool attr = false;
@@ -118,10 +120,19 @@ int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, _
     attr = true;
   }
   TG_CHECK(smem <= 96 * 1024, "conv_in: Cout=%d too large", Cout);
-  TG_CUDA(launch_kernel(kern, dim3((H * W + PIX - 1) / PIX, B), dim3(256), smem, st, 1, x, w, bias, y, H, W, Cout));
+  TG_CUDA(launch_kernel(kern, dim3((H * W + PIX - 1) / PIX, B), dim3(256), smem, st, 1, x, w, bias, y, H, W, Cout, silu));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
+}
+
+// Cin = 4: the UNet / ControlNet conv_in on latents; Cin = 3: the first convolution of the ControlNet conditioning
+// embedder on the RGB hint image (diffusers ControlNetConditioningEmbedding.conv_in, followed by SiLU).
+int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int H, int W,
+                         int Cout, int silu, cudaStream_t st) {
+  if (Cin == 4) return conv_in_launch<4>(x, w, bias, y, B, H, W, Cout, silu, st);
+  if (Cin == 3) return conv_in_launch<3>(x, w, bias, y, B, H, W, Cout, silu, st);
+  TG_CHECK(false, "conv_in: Cin=%d unsupported (3 or 4)", Cin);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -26,6 +26,9 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
 
 // allocates the per-device split-K workspace (call once outside stream capture; lazily done otherwise)
 int gemm_init();
+// measurement hook: when non-null every GEMM CTA writes 8 counters {main-loop cycles, producer wait, MMA wait(full),
+// MMA wait(accumulator), epilogue wait, k-blocks, tiles, -} at dev_buf[blockIdx.x*8..] (tools/gemm_probe.py)
+void gemm_set_prof(long long* dev_buf);
 
 // GroupNorm(32 groups)(+SiLU) over the channel-concat [x1 | x2] (x2 may be null, C2 = 0); fp32 statistics.
 // workspace: >= B*64*32*2 floats.
@@ -51,8 +54,8 @@ int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half*
 
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaStream_t st);
-int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W,
-                         int Cout, cudaStream_t st);
+int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int H, int W,
+                         int Cout, int silu, cudaStream_t st);
 int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
                           cudaStream_t st);
 int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st);

@@ -93,7 +93,7 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
     return out
 
 
-def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, out_scale=1.0, out=None):
+def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, out_scale=1.0, out=None):
     """x [B,H,W,Cin] NHWC, w [Cout,3,3,Cin] -> [B,H,W,Cout] (pad 1, stride 1)."""
     _chk16(x, w, bias, rowbias, residual, out)
     B, H, W, Cin = x.shape
@@ -107,7 +107,7 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, out_scale=1.0, out=
                 2.0 * (Mc * Cin + Cout * 9 * Cin + Mc * Cout + (Mc * Cout if res2 is not None else 0)),
                 lambda: _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
                                0 if rowbias is None else rowbias.stride(0), _p(res2),
-                               0 if res2 is None else res2.stride(0), float(out_scale), _p(out), Cout, _stream()))
+                               0 if res2 is None else res2.stride(0), act, float(out_scale), _p(out), Cout, _stream()))
     _lib.check(rc, "tg_conv3x3")
     return out
 
@@ -223,14 +223,16 @@ def im2col_s2(x, out=None):
     return out
 
 
-def conv_in(x_nchw, w, bias, out=None):
+def conv_in(x_nchw, w, bias, out=None, silu=False):
+    """x NCHW [B,Cin,H,W] (Cin 3 or 4), w [Cout,Cin,3,3] (torch layout) -> NHWC [B,H,W,Cout]."""
     _chk16(x_nchw, w, bias, out)
     B, Cin, H, W = x_nchw.shape
-    assert Cin == 4 and x_nchw.is_contiguous() and w.is_contiguous()
+    assert Cin in (3, 4) and x_nchw.is_contiguous() and w.is_contiguous() and w.shape[1] == Cin
     Cout = w.shape[0]
     if out is None:
         out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x_nchw.device)
-    _lib.check(_lib.lib().tg_conv_in(_p(x_nchw), _p(w), _p(bias), _p(out), B, H, W, Cout, _stream()), "tg_conv_in")
+    _lib.check(_lib.lib().tg_conv_in(_p(x_nchw), _p(w), _p(bias), _p(out), B, Cin, H, W, Cout, int(silu), _stream()),
+               "tg_conv_in")
     return out
 
 
