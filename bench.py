@@ -10,15 +10,17 @@ SD-1.5 512x512, 4 characters with layout masks + attention-guidance energy, 50 D
 One bench "step" is one timestep index of a turn:
     * the stage-1 denoise step of the 4 co-batched characters (one B=8 UNet forward, per-sample IP scales
       0.0/0.4/0.4/0.4, fused CFG+DDIM)                                          = 4 denoise steps
-    * the stage-2 denoise step of the composed image (B=2 UNet forward, IP scale 0.1, fused CFG+DDIM+masked
-      composite, capture of the 4 guidance attention maps + guidance energy for index < 30)  = 1 denoise step
+    * the stage-2 denoise step of the composed image (B=2 ControlNet-lineart forward feeding its 13 residuals into a
+      B=2 UNet forward, IP scale 0.1, fused CFG+DDIM+masked composite, capture of the 4 guidance attention maps +
+      guidance energy for index < 30)                                            = 1 denoise step
 so value = 5 * K / seconds (x ranks; every rank owns independent dialogues -> weak scaling, no data-path
 collective; the UNet/IP weights are NCCL-broadcast from rank 0 once at start-up).
 By default the five trajectories share ONE UNet forward of batch 10 (per-sample IP scale; composite, capture and
 energy apply to the stage-2 trajectory only): in steady state a rank always holds a turn in stage 1 and another
 dialogue's turn in stage 2 (config 5: 8 dialogues per GPU), and co-batching them is a scheduling decision, not a
 change of arithmetic.  `--separate-stage2` runs the two forwards as separate graphs (B=8 then B=2) instead.
-ControlNet residuals of stage 2 are outside this round's scope and are not computed.
+The stage-2 ControlNet (reference models/pipelines.py:770-778) runs on our kernels inside the same
+graph; its timestep-independent conditioning embedder runs once per trajectory (at index 0, inside the timed region).
 """
 import argparse
 import json
@@ -32,11 +34,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_DENOISE_STEP = 1.607e12  # one B=2 UNet forward, 81 context tokens
+FLOPS_CONTROLNET_STEP = 0.523e12   # ControlNet encoder + mid + zero-convs per stage-2 step (B=2)
 KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]
 XYWH = [[278, 251, 157, 185], [358, 328, 150, 180], [168, 4, 100, 80], [4, 331, 80, 70]]  # CMIGBench dialogue 4
 WORKLOAD = ("sd15-512x512, 4 characters (stage-1 co-batched B=8, ip_scale 0/0.4/0.4/0.4) + stage-2 composite step "
-            "(B=2, ip_scale 0.1, layout mask, 4-map guidance energy for index<30), 50 DDIM steps, cfg 7.5, "
-            "ctx 77+4 tokens")
+            "(B=2 ControlNet-lineart + UNet, ip_scale 0.1, layout mask, 4-map guidance energy for index<30), "
+            "50 DDIM steps, cfg 7.5, ctx 77+4 tokens")
 
 
 def peaks():
@@ -142,6 +145,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from theatergen_b200 import _lib, ops, synth
+    from theatergen_b200.controlnet import TGControlNet
     from theatergen_b200.engine import DenoiseEngine
     from theatergen_b200.unet import TGUNet
     from theatergen_b200.utils.guidance import EnergyPlan
@@ -158,19 +162,26 @@ def run_ours(args):
     _lib.lib()  # fail loudly if the extension is missing
 
     # ---- weights: rank 0 generates, NCCL broadcast to the others (the only collective on this path) ----
-    sd = synth.synth_state_dict(dev, 1234, fill=(rank == 0))
-    if world > 1:
-        flat = torch.cat([v.reshape(-1) for v in sd.values()])
-        dist.broadcast(flat, 0)
-        off = 0
-        for k, v in sd.items():
-            sd[k] = flat[off:off + v.numel()].view_as(v)
-            off += v.numel()
-    net = TGUNet(sd, dev)
-    del sd
-    eng = DenoiseEngine(net)
+    def shared(sd):
+        if world > 1:
+            flat = torch.cat([v.reshape(-1) for v in sd.values()])
+            dist.broadcast(flat, 0)
+            off = 0
+            for k, v in sd.items():
+                sd[k] = flat[off:off + v.numel()].view_as(v)
+                off += v.numel()
+        return sd
+
+    net = TGUNet(shared(synth.synth_state_dict(dev, 1234, fill=(rank == 0))), dev)
+    cnet = TGControlNet(shared(synth.synth_controlnet_state_dict(dev, 4321, fill=(rank == 0))), dev)
+    eng = DenoiseEngine(net, controlnet=cnet)
     K, STEPS = 4, 50
     ctx1, ctx2, lat1, lat2, x0, nz, scale1 = build_inputs(torch, dev, K)
+    # synthetic line-art hint of the collage (stand-in for LineartDetector output): sparse strokes in [0,1]
+    hint = (torch.rand(1, 1, 512, 512, generator=torch.Generator().manual_seed(99)) > 0.93).half().repeat(1, 3, 1, 1)
+    h_hint = hint.contiguous().pin_memory()
+    d_hint = hint.to(dev)
+    ctrl_ctx = ctx2[:, :77].contiguous()  # the ControlNet sees the 77 text tokens only
     ts, coef = eng.tables(STEPS, 7.5)
     sched = eng.scheduler
     frozen_all = torch.cat([lat2.float()] + [sched.add_noise(x0, nz, torch.tensor([int(t)])) for t in sched.timesteps]).half()
@@ -200,7 +211,7 @@ def run_ours(args):
 
     class Stage2(StepGraph):
         def __init__(self, energy):
-            super().__init__(eng, 1, 81, True, KEYS)
+            super().__init__(eng, 1, 81, True, KEYS, controlnet=True)
             self.energy = energy
 
         def _body(self):
@@ -213,20 +224,34 @@ def run_ours(args):
     mixed = not args.separate_stage2
     gme = gm = None
     if mixed:
-        gme = MixedStepGraph(eng, K, 1, 81, KEYS, plan).capture()
-        gm = MixedStepGraph(eng, K, 1, 81, None, None).capture()
-        for g in (gme, gm):
-            g.ctx.copy_(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
-            g.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4, 0.1] * 2))
+        gme = MixedStepGraph(eng, K, 1, 81, KEYS, plan, controlnet=True).capture()
+        gm = MixedStepGraph(eng, K, 1, 81, None, None, controlnet=True).capture()
+        for g in (gme, gm):  # batch rows: [stage-1 uncond | stage-1 cond | stage-2 uncond | stage-2 cond]
+            g.ctx.copy_(torch.cat([ctx1, ctx2]))
+            g.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2 + [0.1, 0.1]))
             g.latents.copy_(torch.cat([lat1, lat2]))
             g.mask.copy_(h_mask)
-        h_ctxm = pin(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
+            g.ctrl_ctx.copy_(ctrl_ctx)
+        h_ctxm = pin(torch.cat([ctx1, ctx2]))
+        h_ctrl = pin(ctrl_ctx)
         h_latm = pin(torch.cat([lat1, lat2]))
         h_tsm = pin(ts.cpu()[:, None].repeat(1, 2 * (K + 1)))
         h_outm = torch.empty((K + 1, 4, 64, 64), dtype=torch.float16).pin_memory()
     g1.ctx.copy_(h_ctx1); g1.ip_scale.copy_(scale1); g1.latents.copy_(h_lat1)
     for g in (g2e, g2):
         g.ctx.copy_(h_ctx2); g.ip_scale.fill_(0.1); g.latents.copy_(h_lat2); g.mask.copy_(h_mask)
+        g.ctrl_ctx.copy_(ctrl_ctx)
+    stage2_graphs = (gme, gm) if mixed else (g2e, g2)
+
+    def embed_hint(src):
+        """per-trajectory ControlNet work: conditioning embedder on the hint image (timestep independent)"""
+        emb = cnet.embed_condition(src)
+        for g in stage2_graphs:
+            g.cond_emb.copy_(emb)
+
+    n0 = _lib.launch_count()
+    embed_hint(d_hint)
+    embed_launches = _lib.launch_count() - n0
     torch.cuda.synchronize()
     launches_per_step = {True: g1.launches_per_step + g2e.launches_per_step,
                          False: g1.launches_per_step + g2.launches_per_step}
@@ -235,6 +260,8 @@ def run_ours(args):
 
     def step_device_mixed(i):
         idx = i % STEPS
+        if idx == 0:
+            embed_hint(d_hint)
         g = gme if idx < 30 else gm
         g.t.copy_(d_ts[idx].expand(2 * (K + 1))); g.coef.copy_(d_coef[idx]); g.frozen.copy_(d_frozen[idx + 1])
         g.replay()
@@ -250,6 +277,9 @@ def run_ours(args):
             gme.ctx.copy_(h_ctxm, non_blocking=True); gm.ctx.copy_(h_ctxm, non_blocking=True)
             gme.latents.copy_(h_latm, non_blocking=True); gme.mask.copy_(h_mask, non_blocking=True)
             gm.mask.copy_(h_mask, non_blocking=True)
+            gme.ctrl_ctx.copy_(h_ctrl, non_blocking=True); gm.ctrl_ctx.copy_(h_ctrl, non_blocking=True)
+            d_hint.copy_(h_hint, non_blocking=True)
+            embed_hint(d_hint)
         g.t.copy_(h_tsm[idx], non_blocking=True); g.coef.copy_(h_coef[idx], non_blocking=True)
         g.frozen.copy_(h_frozen[idx + 1], non_blocking=True)
         g.replay()
@@ -263,6 +293,8 @@ def run_ours(args):
     def step_device(i):
         """inputs resident in HBM; only device-side work"""
         idx = i % STEPS
+        if idx == 0:
+            embed_hint(d_hint)
         g1.t.copy_(d_ts[idx].expand(2 * K)); g1.coef.copy_(d_coef[idx])
         g1.replay()
         g = g2e if idx < 30 else g2
@@ -285,6 +317,8 @@ def run_ours(args):
             for g in (g2e, g2):
                 g.ctx.copy_(h_ctx2, non_blocking=True); g.latents.copy_(h_lat2, non_blocking=True)
                 g.mask.copy_(h_mask, non_blocking=True)
+            d_hint.copy_(h_hint, non_blocking=True)
+            embed_hint(d_hint)
         g1.replay()
         g = g2e if idx < 30 else g2
         g.t.copy_(h_ts2[idx], non_blocking=True); g.coef.copy_(h_coef[idx], non_blocking=True)
@@ -327,7 +361,8 @@ def run_ours(args):
     ms_dev = timed(step_device_mixed if mixed else step_device, Kb, Wb)
     clocks = sampler.stop() if rank == 0 else None
     n_energy = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) < 30)
-    gpu_launches = n_energy * launches_per_step[True] + (Kb - n_energy) * launches_per_step[False]
+    n_embed = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) == 0)
+    gpu_launches = n_energy * launches_per_step[True] + (Kb - n_energy) * launches_per_step[False] + n_embed * embed_launches
     ms_e2e = timed(step_e2e_mixed if mixed else step_e2e, Kb, Wb)
 
     # ---- replay time of each captured graph on its own (where the step time goes) ----
@@ -409,7 +444,8 @@ def run_ours(args):
         denoise_per_step = (K + 1) * world
         value = denoise_per_step * Kb / (ms_dev * 1e-3)
         e2e = denoise_per_step * Kb / (ms_e2e * 1e-3)
-        h2d = 8 * 4 + 8 * 4 + 4 * 64 * 64 * 2 + (h_ctx1.numel() + h_ctx2.numel() + h_lat1.numel() + h_lat2.numel() + h_mask.numel()) * 2 // STEPS
+        h2d = 8 * 4 + 8 * 4 + 4 * 64 * 64 * 2 + (h_ctx1.numel() + h_ctx2.numel() + h_lat1.numel() + h_lat2.numel() + h_mask.numel()
+                                                 + ctrl_ctx.numel() + h_hint.numel()) * 2 // STEPS
         d2h = (K + 1) * 4 * 64 * 64 * 2 + 4
         out = {
             "metric": "denoise-steps/sec", "value": round(value, 2), "unit": "steps/s", "n_gpus": world,
@@ -417,12 +453,14 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "denoise_steps_per_bench_step_per_gpu": K + 1,
                        "l2_policy": "inputs larger than L2 (1.76 GB of weights streamed per forward vs 126 MB L2)",
-                       "cuda_graphs": True, "cobatch_stage1_stage2": mixed, "controlnet": "not computed (out of scope this round)",
+                       "cuda_graphs": True, "cobatch_stage1_stage2": mixed,
+                       "controlnet": "computed on our kernels inside the stage-2 forward (conditioning embedder once per trajectory)",
                        "parallelism": f"dp{world} (independent dialogues per rank, weights NCCL-broadcast once)"},
             "e2e": {"value": round(e2e, 2), "unit": "steps/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(ms_e2e / Kb, 4)},
             "gpu_launches": int(gpu_launches), "clocks": clocks,
-            "tensor_frac_of_step": round(value / world * FLOPS_PER_DENOISE_STEP / 1e12 / peaks()[0], 4),
+            "tensor_frac_of_step": round(Kb / (ms_dev * 1e-3) * (K * FLOPS_PER_DENOISE_STEP + FLOPS_PER_DENOISE_STEP
+                                                                + FLOPS_CONTROLNET_STEP) / 1e12 / peaks()[0], 4),
             "roofline": roof, "cpu_baseline": cpu, "graph_replay_ms": graphs,
             "kernel_breakdown_per_forward": breakdown,
         }

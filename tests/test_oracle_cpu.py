@@ -137,3 +137,34 @@ def test_unet_structure():
     # processor order = IP-Adapter checkpoint index order 1,3,..,31 (ip_adapter/ip_adapter.py:139-140)
     keys = [k for _, _, k in OU.transformer_specs()]
     assert keys[0] == ("down", 0, 0, 0) and keys[6] == ("up", 1, 0, 0) and keys[-1] == ("mid", 0, 0, 0)
+
+
+def test_controlnet_oracle_structure_and_determinism():
+    """oracle/controlnet.py: diffusers ControlNetModel key set with the published SD-1.5 parameter count
+    (361,279,120), residual shapes that line up with the UNet's 12 skips + mid, zero 'zero-convs' -> zero residuals."""
+    from oracle import controlnet as OC
+    from oracle import unet as OU
+    sd = OC.synth_state_dict(4321)
+    assert sum(v.numel() for v in sd.values()) == 361_279_120
+    assert not any(k.startswith("up_blocks") or k.startswith("conv_out") for k in sd)
+    g = torch.Generator().manual_seed(0)
+    x, ctx = torch.randn(2, 4, 64, 64, generator=g), torch.randn(2, 77, 768, generator=g)
+    cond = torch.rand(2, 3, 512, 512, generator=g)
+    for k in list(sd):
+        if k.startswith(("controlnet_down_blocks", "controlnet_mid_block")):
+            sd[k] = torch.zeros_like(sd[k])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        emb = OC.cond_embedding(sd, cond)
+        down, mid = OC.controlnet_forward(sd, x, 981, ctx, cond)
+    assert emb.shape == (2, 320, 64, 64)
+    want = [(320, 64)] * 3 + [(320, 32)] + [(640, 32)] * 2 + [(640, 16)] + [(1280, 16)] * 2 + [(1280, 8)] * 3
+    assert [(t.shape[1], t.shape[2]) for t in down] == want and mid.shape == (2, 1280, 8, 8)
+    assert all(float(t.abs().max()) == 0 for t in down) and float(mid.abs().max()) == 0
+    # zero residuals leave the UNet unchanged (unet_2d_condition.py:1044-1053)
+    sdu = OU.synth_state_dict(1234)
+    ctx81 = torch.cat([ctx, torch.randn(2, 4, 768, generator=g)], 1)
+    with torch.no_grad():
+        a = OU.unet_forward(sdu, x, 981, ctx81, ip_scale=0.1)
+        b = OU.unet_forward(sdu, x, 981, ctx81, ip_scale=0.1, down_residuals=down, mid_residual=mid)
+    assert torch.equal(a, b)

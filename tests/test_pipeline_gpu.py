@@ -176,8 +176,9 @@ def test_cobatched_stage1_stage2_step_matches_separate_steps():
     plan = EnergyPlan([[0.1, 0.2, 0.6, 0.7]], [[3, 4]], keys, fg_weight=1.0, bg_weight=4.0)
     ts, coef = eng.tables(50, 7.5)
     mx = MixedStepGraph(eng, K, 1, 81, keys, plan)
-    mx.latents.copy_(torch.cat([lat1, lat2])); mx.ctx.copy_(torch.cat([ctx1[:K], ctx2[:1], ctx1[K:], ctx2[1:]]))
-    mx.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4, 0.1] * 2)); mx.frozen.copy_(frozen); mx.mask.copy_(mask.half())
+    # batch rows: [stage-1 uncond | stage-1 cond | stage-2 uncond | stage-2 cond]
+    mx.latents.copy_(torch.cat([lat1, lat2])); mx.ctx.copy_(torch.cat([ctx1, ctx2]))
+    mx.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2 + [0.1, 0.1])); mx.frozen.copy_(frozen); mx.mask.copy_(mask.half())
     mx.t.copy_(ts[3].expand(10)); mx.coef.copy_(coef[3])
     mx._body()
     s1 = eng.step_graph(K, 81, False)

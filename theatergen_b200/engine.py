@@ -2,8 +2,8 @@
 (+ masked composite) -> trace, with K co-batched characters (batch 2K, per-sample IP scale) and the whole step
 replayed as a CUDA graph.
 
-Mirrors the two loops of the reference: models/pipelines.py:406-453 (stage 1) and :742-835 (stage 2; the
-ControlNet call is outside this round's scope and its residuals can be injected through TGUNet directly).
+Mirrors the two loops of the reference: models/pipelines.py:406-453 (stage 1) and :742-835 (stage 2: ControlNet
+(TGControlNet, fused into the UNet forward) -> UNet -> CFG -> DDIM -> masked composite).
 The reference's per-step `latents.cpu()` (pipelines.py:449-453, 835) becomes an asynchronous device->pinned-host
 copy that is only waited for at the end of the trajectory.
 """
@@ -19,9 +19,15 @@ from .unet import TGUNet
 class StepGraph:
     """One denoise step for a fixed (K, frozen?) shape, captured once and replayed with new t / coefficients."""
 
-    def __init__(self, engine, K, T, composite, capture_keys=None):
+    def __init__(self, engine, K, T, composite, capture_keys=None, controlnet=False):
         dev = engine.device
         self.K = K
+        self.use_controlnet = bool(controlnet)
+        if self.use_controlnet:
+            if engine.controlnet is None:
+                raise RuntimeError("StepGraph(controlnet=True) needs DenoiseEngine.controlnet (a TGControlNet)")
+            self.ctrl_ctx = torch.zeros((2 * K, 77, 768), dtype=torch.float16, device=dev)   # text-only embeddings
+            self.cond_emb = torch.zeros((K, 64, 64, 320), dtype=torch.float16, device=dev)   # embed_condition() output
         self.latents = torch.zeros((K, 4, 64, 64), dtype=torch.float16, device=dev)
         self.x_in = torch.zeros((2 * K, 4, 64, 64), dtype=torch.float16, device=dev)
         self.ctx = torch.zeros((2 * K, T, 768), dtype=torch.float16, device=dev)
@@ -37,11 +43,17 @@ class StepGraph:
         self.graph = None
         self.launches_per_step = 0
 
+    def _control(self, r0, r1):
+        if not self.use_controlnet:
+            return None, None
+        return self.engine.controlnet, dict(rows=(r0, r1), ctx=self.ctrl_ctx, cond_emb=self.cond_emb)
+
     def _body(self):
         net = self.engine.unet
         ops.duplicate_latents(self.latents, self.x_in)
+        cn, control = self._control(0, 2 * self.K)
         eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
-                              save_keys=self.capture_keys, cond_only=True)
+                              save_keys=self.capture_keys, cond_only=True, controlnet=cn, control=control)
         ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
                                latents_copy=self.trace)
 
@@ -67,12 +79,15 @@ class StepGraph:
 
 class MixedStepGraph(StepGraph):
     """One denoise step for a co-batch of K1 stage-1 trajectories (plain CFG + DDIM) and K2 stage-2 trajectories
-    (masked composite, optional capture of the guidance maps + energy): independent trajectories of different
-    turns / dialogues that happen to sit at the same timestep index share ONE UNet forward of batch 2*(K1+K2) with
-    per-sample IP scale.  `energy_plan` (utils.guidance.EnergyPlan) is evaluated on the first stage-2 trajectory."""
+    (ControlNet residuals, masked composite, optional capture of the guidance maps + energy): independent trajectories
+    of different turns / dialogues that happen to sit at the same timestep index share ONE UNet forward of batch
+    2*(K1+K2) with per-sample IP scale.  Batch rows: [stage-1 uncond K1 | stage-1 cond K1 | stage-2 uncond K2 |
+    stage-2 cond K2] -- `ctx`, `ip_scale`, `t` follow that order; the stage-2 rows are contiguous so the ControlNet
+    (batch 2*K2) adds its residuals into a row range of the skip tensors.  `latents` / `trace` are [K1 + K2].
+    `energy_plan` (utils.guidance.EnergyPlan) is evaluated on the first stage-2 trajectory."""
 
-    def __init__(self, engine, K1, K2, T, capture_keys=None, energy_plan=None):
-        super().__init__(engine, K1 + K2, T, False, capture_keys)
+    def __init__(self, engine, K1, K2, T, capture_keys=None, energy_plan=None, controlnet=False):
+        super().__init__(engine, K1 + K2, T, False, capture_keys, controlnet=False)
         dev = engine.device
         self.K1, self.K2 = K1, K2
         self.frozen = torch.zeros((K2, 4, 64, 64), dtype=torch.float16, device=dev)
@@ -80,23 +95,32 @@ class MixedStepGraph(StepGraph):
         self.energy_plan = energy_plan
         self.loss = torch.zeros((1,), dtype=torch.float32, device=dev)
         self._ws = torch.empty((256,), dtype=torch.float32, device=dev)
+        self.use_controlnet = bool(controlnet)
+        if self.use_controlnet:
+            if engine.controlnet is None:
+                raise RuntimeError("MixedStepGraph(controlnet=True) needs DenoiseEngine.controlnet (a TGControlNet)")
+            self.ctrl_ctx = torch.zeros((2 * K2, 77, 768), dtype=torch.float16, device=dev)
+            self.cond_emb = torch.zeros((K2, 64, 64, 320), dtype=torch.float16, device=dev)
 
     def _body(self):
         net = self.engine.unet
-        ops.duplicate_latents(self.latents, self.x_in)
-        eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
-                              save_keys=self.capture_keys, cond_only=True)
-        if self.energy_plan is not None:
-            self.energy_plan.run([self.captured[k][self.K1] for k in self.capture_keys], self.loss, self._ws)
         K1, K2 = self.K1, self.K2
-        ops.cfg_ddim_composite(eps, self.latents, self.coef, latents_copy=self.trace[:K1], k0=0, count=K1)
-        ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
-                               latents_copy=self.trace[K1:], k0=K1, count=K2)
+        ops.duplicate_latents(self.latents[:K1], self.x_in[:2 * K1])
+        ops.duplicate_latents(self.latents[K1:], self.x_in[2 * K1:])
+        cn, control = self._control(2 * K1, 2 * (K1 + K2))
+        eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
+                              save_keys=self.capture_keys, capture_b0=2 * K1 + K2, controlnet=cn, control=control)
+        if self.energy_plan is not None:
+            self.energy_plan.run([self.captured[k][0] for k in self.capture_keys], self.loss, self._ws)
+        ops.cfg_ddim_composite(eps[:2 * K1], self.latents[:K1], self.coef, latents_copy=self.trace[:K1])
+        ops.cfg_ddim_composite(eps[2 * K1:], self.latents[K1:], self.coef, frozen=self.frozen, mask=self.mask,
+                               latents_copy=self.trace[K1:])
 
 
 class DenoiseEngine:
-    def __init__(self, unet: TGUNet, scheduler: DDIMScheduler | None = None, use_graphs=True):
+    def __init__(self, unet: TGUNet, scheduler: DDIMScheduler | None = None, use_graphs=True, controlnet=None):
         self.unet = unet
+        self.controlnet = controlnet  # optional TGControlNet (stage 2)
         self.device = unet.device
         self.scheduler = scheduler or DDIMScheduler()
         self.use_graphs = use_graphs
@@ -112,10 +136,10 @@ class DenoiseEngine:
             self._tables[key] = (ts, coef)
         return self._tables[key]
 
-    def step_graph(self, K, T, composite, capture_keys=None):
-        key = (K, T, composite, tuple(capture_keys) if capture_keys else None)
+    def step_graph(self, K, T, composite, capture_keys=None, controlnet=False):
+        key = (K, T, composite, tuple(capture_keys) if capture_keys else None, bool(controlnet))
         if key not in self._graphs:
-            sg = StepGraph(self, K, T, composite, capture_keys)
+            sg = StepGraph(self, K, T, composite, capture_keys, controlnet=controlnet)
             if self.use_graphs:
                 sg.capture()
             self._graphs[key] = sg
@@ -123,17 +147,23 @@ class DenoiseEngine:
 
     @torch.no_grad()
     def denoise(self, latents, ctx, ip_scale, num_steps=50, guidance_scale=7.5, frozen_all=None, frozen_mask=None,
-                frozen_steps=0, trace_host=None, capture_keys=None, on_step=None):
+                frozen_steps=0, trace_host=None, capture_keys=None, on_step=None, control_ctx=None, cond_emb=None):
         """latents [K,4,64,64], ctx [2K,T,768] (rows [0,K) unconditional), ip_scale float[2K] or float.
         frozen_all [steps+1,K,4,64,64] + frozen_mask [64,64] enable the stage-2 composite for index < frozen_steps.
         trace_host: optional pinned fp16 [steps+1,K,4,64,64] receiving every step's latents asynchronously.
+        control_ctx [2K,77,768] (text-only embeddings) + cond_emb [K or 1,64,64,320] (TGControlNet.embed_condition
+        of the hint image) switch on the ControlNet of stage 2 (needs self.controlnet).
         Returns the final latents (device)."""
         K, T = latents.shape[0], ctx.shape[1]
         ts, coef = self.tables(num_steps, guidance_scale)
         composite = frozen_all is not None and frozen_steps > 0
-        sg = self.step_graph(K, T, composite, capture_keys)
+        use_cn = control_ctx is not None
+        sg = self.step_graph(K, T, composite, capture_keys, controlnet=use_cn)
         sg.latents.copy_(latents, non_blocking=True)
         sg.ctx.copy_(ctx, non_blocking=True)
+        if use_cn:
+            sg.ctrl_ctx.copy_(control_ctx, non_blocking=True)
+            sg.cond_emb.copy_(cond_emb.expand_as(sg.cond_emb), non_blocking=True)
         if torch.is_tensor(ip_scale):
             sg.ip_scale.copy_(ip_scale.to(torch.float32), non_blocking=True)
         else:
@@ -147,7 +177,10 @@ class DenoiseEngine:
             cur = sg
             if composite and i >= frozen_steps:  # composite only for index < frozen_steps (pipelines.py:833)
                 if sg_plain is None:
-                    sg_plain = self.step_graph(K, T, False, capture_keys)
+                    sg_plain = self.step_graph(K, T, False, capture_keys, controlnet=use_cn)
+                    if use_cn:
+                        sg_plain.ctrl_ctx.copy_(sg.ctrl_ctx)
+                        sg_plain.cond_emb.copy_(sg.cond_emb)
                     sg_plain.ctx.copy_(sg.ctx)
                     sg_plain.ip_scale.copy_(sg.ip_scale)
                     sg_plain.latents.copy_(sg.latents)

@@ -5,8 +5,8 @@ theatergen_b200.engine.DenoiseEngine (CUDA-graph replayed libtheatergen.so kerne
 
 What is NOT re-implemented here and is reached through the objects the caller passes in, exactly like the reference
 does (duck-typed): `adapter.pipe.encode_prompt` (CLIP text), `adapter.pipe.vae` / `image_processor` (VAE),
-`adapter.get_image_embeds(pil_image=...)` (CLIP vision), `controlnetpipe.controlnet` + `processor` (ControlNet and the
-line-art detector).  `basever == 'xl'` raises: SDXL is outside the metric.
+`adapter.get_image_embeds(pil_image=...)` (CLIP vision), `processor` (the line-art detector).  `controlnetpipe.controlnet` is a
+theatergen_b200.controlnet.TGControlNet on the kernel path (any other module is called eagerly per step).  `basever == 'xl'` raises: SDXL is outside the metric.
 
 Reference quirks kept on purpose: the stage-1 prompt is re-encoded from `ip_prompt` and the
 `input_embeddings` argument is ignored (#3); stage 2 overwrites `latents_all[0]`, `latents_all[1:]` and `frozen_mask`
@@ -20,6 +20,7 @@ import warnings
 import numpy as np
 import torch
 
+from ..controlnet import TGControlNet
 from ..engine import DenoiseEngine
 from ..unet import TGUNet
 from ..utils import guidance, schedule
@@ -248,16 +249,28 @@ def final_image_generation(basever, processor, controlnetpipe, tpipe, overall_pr
     if torch.is_tensor(latents_all) and latents_all.shape == frozen.shape:
         latents_all.copy_(frozen)  # the reference mutates the caller's tensor in place (:737-738)
 
-    if controlnetpipe is not None and getattr(controlnetpipe, "controlnet", None) is not None:
-        # ControlNet runs through the caller's module (outside this round's kernels); one forward per step feeds
-        # the residuals into TGUNet.  Not graph-replayed.
+    controlnet = getattr(controlnetpipe, "controlnet", None) if controlnetpipe is not None else None
+    control_ctx = cond_emb = None
+    if isinstance(controlnet, TGControlNet):
+        # ControlNet on our kernels, fused into the UNet forward and graph-replayed (pipelines.py:702-731, 770-778).
+        # The conditioning embedder is timestep independent: it runs once here instead of once per step.
+        control_image = processor(np.array(input_img))
+        imagetight = controlnetpipe.prepare_image(image=control_image, width=width, height=height, batch_size=1,
+                                                  num_images_per_prompt=1, device="cuda", dtype=torch.float16,
+                                                  do_classifier_free_guidance=True, guess_mode=False)
+        cond_emb = controlnet.embed_condition(imagetight[:1])  # the CFG pair shares one hint image
+        control_ctx = input_embeddings[0].to(torch_device, torch.float16)  # [uncond ; cond] x 77 text tokens (:761)
+        eng.controlnet = controlnet
+    elif controlnet is not None:
+        # a foreign ControlNet module (e.g. stock diffusers): one eager forward per step feeds NCHW residuals to TGUNet
         return _stage2_with_controlnet(eng, adapter, controlnetpipe, processor, input_img, input_embeddings, ip_embeds,
                                        latents, frozen, frozen_mask, num_inference_steps, frozen_steps, guidance_scale,
                                        height, width, vae)
     n = num_inference_steps
     trace = torch.empty((n + 1, 1, 4, 64, 64), dtype=torch.float16).pin_memory()
     final = eng.denoise(latents.half(), ip_embeds.half(), 0.1, num_steps=n, guidance_scale=guidance_scale,
-                        frozen_all=frozen.half(), frozen_mask=frozen_mask, frozen_steps=frozen_steps, trace_host=trace)
+                        frozen_all=frozen.half(), frozen_mask=frozen_mask, frozen_steps=frozen_steps, trace_host=trace,
+                        control_ctx=control_ctx, cond_emb=cond_emb)
     latents = final.clone()
     torch.cuda.current_stream().synchronize()
     images = decode(vae, latents)

@@ -51,11 +51,32 @@ def unet_shapes(with_ip=True, cross=768):
     return s
 
 
-def synth_state_dict(device="cuda", seed=1234, with_ip=True, fill=True):
+def controlnet_shapes(cross=768):
+    """diffusers ControlNetModel (SD-1.5) key set: the UNet's encoder half + conditioning embedder + zero convs."""
+    u = unet_shapes(with_ip=False, cross=cross)
+    s = {k: v for k, v in u.items() if not (k.startswith("up_blocks") or k.startswith("conv_norm_out") or k.startswith("conv_out"))}
+    ch = (16, 32, 96, 256)
+    p = "controlnet_cond_embedding"
+    s[p + ".conv_in.weight"], s[p + ".conv_in.bias"] = (ch[0], 3, 3, 3), (ch[0],)
+    for i in range(3):
+        s[f"{p}.blocks.{2 * i}.weight"], s[f"{p}.blocks.{2 * i}.bias"] = (ch[i], ch[i], 3, 3), (ch[i],)
+        s[f"{p}.blocks.{2 * i + 1}.weight"], s[f"{p}.blocks.{2 * i + 1}.bias"] = (ch[i + 1], ch[i], 3, 3), (ch[i + 1],)
+    s[p + ".conv_out.weight"], s[p + ".conv_out.bias"] = (320, ch[3], 3, 3), (320,)
+    for i, c in enumerate((320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280)):
+        s[f"controlnet_down_blocks.{i}.weight"], s[f"controlnet_down_blocks.{i}.bias"] = (c, c, 1, 1), (c,)
+    s["controlnet_mid_block.weight"], s["controlnet_mid_block.bias"] = (1280, 1280, 1, 1), (1280,)
+    return s
+
+
+def synth_controlnet_state_dict(device="cuda", seed=4321, fill=True):
+    return synth_state_dict(device, seed, fill=fill, shapes=controlnet_shapes())
+
+
+def synth_state_dict(device="cuda", seed=1234, with_ip=True, fill=True, shapes=None):
     """fill=False returns uninitialised tensors of the right shapes (ranks that receive the NCCL broadcast)."""
     g = torch.Generator(device=device).manual_seed(seed)
     out = {}
-    for name, shp in unet_shapes(with_ip).items():
+    for name, shp in (shapes or unet_shapes(with_ip)).items():
         if not fill:
             out[name] = torch.empty(shp, dtype=torch.float16, device=device)
             continue
@@ -63,7 +84,7 @@ def synth_state_dict(device="cuda", seed=1234, with_ip=True, fill=True):
             fan_in = 1
             for d in shp[1:]:
                 fan_in *= d
-            scale = 0.5 if name.endswith(("to_out.0.weight", "ff.net.2.weight")) else 1.0
+            scale = 0.5 if name.endswith(("to_out.0.weight", "ff.net.2.weight")) or name.startswith("controlnet_") else 1.0
             t = torch.randn(shp, generator=g, device=device) * (scale / math.sqrt(fan_in))
         elif name.endswith("weight") and ".norm" in name or name == "conv_norm_out.weight":
             t = 1.0 + 0.1 * torch.randn(shp, generator=g, device=device)

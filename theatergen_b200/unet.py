@@ -79,9 +79,156 @@ def _transformer_specs():
     return out
 
 
-class TGUNet:
+def _getter(sd, dev):
+    def g(name):
+        t = sd[name].to(device=dev, dtype=torch.float16).contiguous()
+        # TMA descriptors / 16-byte vector loads need 16-byte aligned bases (views into a flat broadcast buffer are not)
+        return t.clone() if t.data_ptr() % 16 else t
+    return g
+
+
+def pack_resnet(g, sd, p, cin, co, temb_off):
+    """diffusers ResnetBlock2D parameters -> kernel layouts (conv3x3 [Cout,3,3,Cin], 1x1 shortcut [Cout,Cin])."""
+    r = dict(cin=cin, cout=co, temb_off=temb_off)
+    r["n1g"], r["n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
+    r["c1w"], r["c1b"] = pack_conv3x3(g(p + ".conv1.weight")), g(p + ".conv1.bias")
+    r["n2g"], r["n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
+    r["c2w"], r["c2b"] = pack_conv3x3(g(p + ".conv2.weight")), g(p + ".conv2.bias")
+    if (p + ".conv_shortcut.weight") in sd:
+        r["scw"] = g(p + ".conv_shortcut.weight").reshape(co, cin).contiguous()
+        r["scb"] = g(p + ".conv_shortcut.bias")
+    return r, g(p + ".time_emb_proj.weight"), g(p + ".time_emb_proj.bias")
+
+
+def pack_transformer(g, dev, p, c, key, kv_off, has_ip):
+    """Transformer2DModel + BasicTransformerBlock parameters -> kernel layouts; returns (dict, context K/V rows)."""
+    tb_ = p + ".transformer_blocks.0"
+    t = dict(C=c, key=key, kv_off=kv_off)
+    t["ng"], t["nb"] = g(p + ".norm.weight"), g(p + ".norm.bias")
+    t["piw"], t["pib"] = g(p + ".proj_in.weight").reshape(c, c).contiguous(), g(p + ".proj_in.bias")
+    t["pow"], t["pob"] = g(p + ".proj_out.weight").reshape(c, c).contiguous(), g(p + ".proj_out.bias")
+    for n in ("norm1", "norm2", "norm3"):
+        t[n + "g"], t[n + "b"] = g(f"{tb_}.{n}.weight"), g(f"{tb_}.{n}.bias")
+    qkv = [g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"]
+    t["qkv_pad"] = (c // HEADS) < 64  # d = 40: pad every head to 64 rows (zero weights) for the tcgen05 path
+    if t["qkv_pad"]:
+        d_ = c // HEADS
+        padded = torch.zeros((3, HEADS, 64, c), dtype=torch.float16, device=dev)
+        for i_, m_ in enumerate(qkv):
+            padded[i_, :, :d_] = m_.view(HEADS, d_, c)
+        t["qkvw"] = padded.view(3 * HEADS * 64, c).contiguous()
+    else:
+        t["qkvw"] = torch.cat(qkv, 0).contiguous()
+    t["o1w"], t["o1b"] = g(f"{tb_}.attn1.to_out.0.weight"), g(f"{tb_}.attn1.to_out.0.bias")
+    t["q2w"] = g(f"{tb_}.attn2.to_q.weight")
+    t["o2w"], t["o2b"] = g(f"{tb_}.attn2.to_out.0.weight"), g(f"{tb_}.attn2.to_out.0.bias")
+    rows = [g(f"{tb_}.attn2.to_k.weight"), g(f"{tb_}.attn2.to_v.weight")]
+    if has_ip:
+        rows += [g(f"{tb_}.attn2.processor.to_k_ip.weight"), g(f"{tb_}.attn2.processor.to_v_ip.weight")]
+    t["kv_rows"] = len(rows)
+    t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
+    t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
+    return t, rows
+
+
+class _BlockNet:
+    """Execution of the blocks the UNet and the ControlNet share (ResnetBlock2D, Transformer2DModel, the time
+    embedding and the encoder half), on packed weights held in self.w / self.resnets / self.transformers."""
     dtype = torch.float16
 
+    def _time_and_context(self, t_dev, ctx, B):
+        w = self.w
+        emb = ops.timestep_embedding(t_dev, 320)
+        emb = ops.gemm(emb, w["t1.w"], w["t1.b"], act=ops.TG_ACT_SILU)
+        emb = ops.gemm(emb, w["t2.w"], w["t2.b"], act=ops.TG_ACT_SILU)  # = silu(time_embedding(t)), its only use
+        temb_all = ops.gemm(emb, w["temb.w"], w["temb.b"])
+        ctxkv = ops.gemm(ctx.reshape(B * ctx.shape[1], -1), w["ctxkv.w"])
+        return temb_all, ctxkv
+
+    def _encoder(self, x, temb_all, tf, B, H, W):
+        """conv_in output -> (last down output, 12 skip tensors, h, w): CrossAttnDownBlock2D x3 + DownBlock2D
+        (ip_adapter/unet_2d_blocks.py:1045-1116, 1171-1202)."""
+        w = self.w
+        skips = [x]
+        h_, w_ = H, W
+        for i in range(4):
+            for j in range(2):
+                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all, B, h_, w_)
+                if i < 3:
+                    x = tf(f"down_blocks.{i}.attentions.{j}", x, h_, w_)
+                skips.append(x)
+            if i < 3:
+                c = BLOCK_OUT[i]
+                x = ops.gemm(ops.im2col_s2(x), w[f"down{i}.w"], w[f"down{i}.b"]).view(B, h_ // 2, w_ // 2, c)
+                h_, w_ = h_ // 2, w_ // 2
+                skips.append(x)
+        return x, skips, h_, w_
+
+    def _mid(self, x, temb_all, tf, B, h_, w_):
+        x = self._resnet("mid_block.resnets.0", x, None, temb_all, B, h_, w_)
+        x = tf("mid_block.attentions.0", x, h_, w_)
+        return self._resnet("mid_block.resnets.1", x, None, temb_all, B, h_, w_)
+
+
+    def _resnet(self, p, x1, x2, temb_all, B, H, W):
+        r = self.resnets[p]
+        cin, co = r["cin"], r["cout"]
+        HW = H * W
+        n1 = ops.groupnorm(x1.view(B, HW, -1), r["n1g"], r["n1b"], 1e-5, x2=None if x2 is None else x2.view(B, HW, -1),
+                           silu=True)
+        h = ops.conv3x3(n1.view(B, H, W, cin), r["c1w"], r["c1b"],
+                        rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co])
+        n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True)
+        if "scw" in r:
+            sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
+            sc = sc.view(B, H, W, co)
+        else:
+            assert x2 is None
+            sc = x1
+        return ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc)
+
+    def _transformer(self, p, x, ctxkv, B, H, W, n_text, n_ip, ip_scale, capture, save_keys, cond_only, token_idx,
+                     capture_b0=None):
+        t = self.transformers[p]
+        C, M = t["C"], B * H * W
+        n = ops.groupnorm(x.view(B, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
+        h = ops.gemm(n.view(M, C), t["piw"], t["pib"])
+        # self attention
+        ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
+        qkv = ops.gemm(ln, t["qkvw"])
+        if t["qkv_pad"] and (H * W) % 128 == 0:
+            P = HEADS * 64
+            a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], B, HEADS, C // HEADS)
+        elif t["qkv_pad"]:
+            raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
+        else:
+            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
+        h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
+        # cross attention (+ image tokens)
+        ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
+        q = ops.gemm(ln, t["q2w"])
+        o = t["kv_off"]
+        probs, b0 = None, 0
+        if capture is not None and (save_keys is None or t["key"] in save_keys):
+            b0 = capture_b0 if capture_b0 is not None else (B // 2 if cond_only else 0)
+            probs = torch.empty((B - b0, HEADS, H * W, n_text), dtype=torch.float16, device=x.device)
+        a = ops.attention_cross_ip(q, ctxkv[:, o:o + C], ctxkv[:, o + C:o + 2 * C],
+                                   ctxkv[:, o + 2 * C:o + 3 * C] if n_ip else None,
+                                   ctxkv[:, o + 3 * C:o + 4 * C] if n_ip else None, B, HEADS, n_text, n_ip,
+                                   ip_scale=ip_scale if n_ip else None, probs=probs, probs_b0=b0)
+        if probs is not None:
+            if token_idx is not None:
+                probs = probs[..., token_idx:token_idx + 1] if isinstance(token_idx, int) else probs[..., token_idx]
+            capture[t["key"]] = probs
+        h = ops.gemm(a, t["o2w"], t["o2b"], residual=h)
+        # feed forward (GEGLU fused in the GEMM epilogue)
+        ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
+        ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
+        h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
+        return ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C)).view(B, H, W, C)
+
+
+class TGUNet(_BlockNet):
     def __init__(self, state_dict, device="cuda", num_ip_tokens=4, cross_attention_dim=768):
         self.device = torch.device(device)
         self.num_ip_tokens = num_ip_tokens
@@ -99,12 +246,7 @@ class TGUNet:
     # -------------------------------------------------------------------------------------------------
     def _pack(self, sd):
         dev = self.device
-
-        def g(name):
-            t = sd[name].to(device=dev, dtype=torch.float16).contiguous()
-            # TMA descriptors / 16-byte vector loads need 16-byte aligned bases (views into a flat broadcast buffer are not)
-            return t.clone() if t.data_ptr() % 16 else t
-
+        g = _getter(sd, dev)
         w = {}
         w["conv_in.w"], w["conv_in.b"] = g("conv_in.weight"), g("conv_in.bias")
         w["t1.w"], w["t1.b"] = g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias")
@@ -112,59 +254,24 @@ class TGUNet:
         self.resnets = {}
         tw, tb, off = [], [], 0
         for p, c1, c2, co in _resnet_specs():
-            cin = c1 + c2
-            r = dict(cin=cin, cout=co, temb_off=off)
-            r["n1g"], r["n1b"] = g(p + ".norm1.weight"), g(p + ".norm1.bias")
-            r["c1w"], r["c1b"] = pack_conv3x3(g(p + ".conv1.weight")), g(p + ".conv1.bias")
-            r["n2g"], r["n2b"] = g(p + ".norm2.weight"), g(p + ".norm2.bias")
-            r["c2w"], r["c2b"] = pack_conv3x3(g(p + ".conv2.weight")), g(p + ".conv2.bias")
-            if (p + ".conv_shortcut.weight") in sd:
-                r["scw"] = g(p + ".conv_shortcut.weight").reshape(co, cin).contiguous()
-                r["scb"] = g(p + ".conv_shortcut.bias")
-            tw.append(g(p + ".time_emb_proj.weight"))
-            tb.append(g(p + ".time_emb_proj.bias"))
+            self.resnets[p], tw_, tb_ = pack_resnet(g, sd, p, c1 + c2, co, off)
+            tw.append(tw_)
+            tb.append(tb_)
             off += co
-            self.resnets[p] = r
         w["temb.w"], w["temb.b"] = torch.cat(tw, 0).contiguous(), torch.cat(tb, 0).contiguous()
         self.transformers = {}
         kvw, off = [], 0
         has_ip = any(k.endswith("processor.to_k_ip.weight") for k in sd)
         self.has_ip = has_ip
         for p, c, key in _transformer_specs():
-            tb_ = p + ".transformer_blocks.0"
-            t = dict(C=c, key=key, kv_off=off)
-            t["ng"], t["nb"] = g(p + ".norm.weight"), g(p + ".norm.bias")
-            t["piw"], t["pib"] = g(p + ".proj_in.weight").reshape(c, c).contiguous(), g(p + ".proj_in.bias")
-            t["pow"], t["pob"] = g(p + ".proj_out.weight").reshape(c, c).contiguous(), g(p + ".proj_out.bias")
-            for n in ("norm1", "norm2", "norm3"):
-                t[n + "g"], t[n + "b"] = g(f"{tb_}.{n}.weight"), g(f"{tb_}.{n}.bias")
-            qkv = [g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"]
-            t["qkv_pad"] = (c // HEADS) < 64  # d = 40: pad every head to 64 rows (zero weights) for the tcgen05 path
-            if t["qkv_pad"]:
-                d_ = c // HEADS
-                padded = torch.zeros((3, HEADS, 64, c), dtype=torch.float16, device=dev)
-                for i_, m_ in enumerate(qkv):
-                    padded[i_, :, :d_] = m_.view(HEADS, d_, c)
-                t["qkvw"] = padded.view(3 * HEADS * 64, c).contiguous()
-            else:
-                t["qkvw"] = torch.cat(qkv, 0).contiguous()
-            t["o1w"], t["o1b"] = g(f"{tb_}.attn1.to_out.0.weight"), g(f"{tb_}.attn1.to_out.0.bias")
-            t["q2w"] = g(f"{tb_}.attn2.to_q.weight")
-            t["o2w"], t["o2b"] = g(f"{tb_}.attn2.to_out.0.weight"), g(f"{tb_}.attn2.to_out.0.bias")
-            rows = [g(f"{tb_}.attn2.to_k.weight"), g(f"{tb_}.attn2.to_v.weight")]
-            if has_ip:
-                rows += [g(f"{tb_}.attn2.processor.to_k_ip.weight"), g(f"{tb_}.attn2.processor.to_v_ip.weight")]
+            self.transformers[p], rows = pack_transformer(g, dev, p, c, key, off, has_ip)
             kvw += rows
             off += c * len(rows)
-            t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
-            t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
-            self.transformers[p] = t
         w["ctxkv.w"] = torch.cat(kvw, 0).contiguous()
         for i in range(3):
             c = BLOCK_OUT[i]
             w[f"down{i}.w"] = pack_conv3x3(g(f"down_blocks.{i}.downsamplers.0.conv.weight")).reshape(c, 9 * c)
             w[f"down{i}.b"] = g(f"down_blocks.{i}.downsamplers.0.conv.bias")
-        rev = list(reversed(BLOCK_OUT))
         for i in range(3):
             w[f"up{i}.w"] = pack_conv3x3(g(f"up_blocks.{i}.upsamplers.0.conv.weight"))
             w[f"up{i}.b"] = g(f"up_blocks.{i}.upsamplers.0.conv.bias")
@@ -191,62 +298,6 @@ class TGUNet:
         return 2 * n
 
     # -------------------------------------------------------------------------------------------------
-    def _resnet(self, p, x1, x2, temb_all, B, H, W):
-        r = self.resnets[p]
-        cin, co = r["cin"], r["cout"]
-        HW = H * W
-        n1 = ops.groupnorm(x1.view(B, HW, -1), r["n1g"], r["n1b"], 1e-5, x2=None if x2 is None else x2.view(B, HW, -1),
-                           silu=True)
-        h = ops.conv3x3(n1.view(B, H, W, cin), r["c1w"], r["c1b"],
-                        rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co])
-        n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True)
-        if "scw" in r:
-            sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
-            sc = sc.view(B, H, W, co)
-        else:
-            assert x2 is None
-            sc = x1
-        return ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc)
-
-    def _transformer(self, p, x, ctxkv, B, H, W, n_text, n_ip, ip_scale, capture, save_keys, cond_only, token_idx):
-        t = self.transformers[p]
-        C, M = t["C"], B * H * W
-        n = ops.groupnorm(x.view(B, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
-        h = ops.gemm(n.view(M, C), t["piw"], t["pib"])
-        # self attention
-        ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
-        qkv = ops.gemm(ln, t["qkvw"])
-        if t["qkv_pad"] and (H * W) % 128 == 0:
-            P = HEADS * 64
-            a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], B, HEADS, C // HEADS)
-        elif t["qkv_pad"]:
-            raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
-        else:
-            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
-        h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
-        # cross attention (+ image tokens)
-        ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
-        q = ops.gemm(ln, t["q2w"])
-        o = t["kv_off"]
-        probs, b0 = None, 0
-        if capture is not None and (save_keys is None or t["key"] in save_keys):
-            b0 = B // 2 if cond_only else 0
-            probs = torch.empty((B - b0, HEADS, H * W, n_text), dtype=torch.float16, device=x.device)
-        a = ops.attention_cross_ip(q, ctxkv[:, o:o + C], ctxkv[:, o + C:o + 2 * C],
-                                   ctxkv[:, o + 2 * C:o + 3 * C] if n_ip else None,
-                                   ctxkv[:, o + 3 * C:o + 4 * C] if n_ip else None, B, HEADS, n_text, n_ip,
-                                   ip_scale=ip_scale if n_ip else None, probs=probs, probs_b0=b0)
-        if probs is not None:
-            if token_idx is not None:
-                probs = probs[..., token_idx:token_idx + 1] if isinstance(token_idx, int) else probs[..., token_idx]
-            capture[t["key"]] = probs
-        h = ops.gemm(a, t["o2w"], t["o2b"], residual=h)
-        # feed forward (GEGLU fused in the GEMM epilogue)
-        ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
-        ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
-        h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
-        return ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C)).view(B, H, W, C)
-
     def _ip_scale_tensor(self, B):
         if self.ip_scale_per_sample is not None:
             assert self.ip_scale_per_sample.numel() == B
@@ -259,8 +310,14 @@ class TGUNet:
 
     # -------------------------------------------------------------------------------------------------
     def forward_raw(self, sample, t_dev, ctx, ip_scale=None, down_residuals=None, mid_residual=None, capture=None,
-                    save_keys=None, cond_only=False, token_idx=None):
-        """sample [B,4,H,W] fp16 (B even), t_dev float32 [B] on device, ctx [B,T,768] fp16 -> eps [B,4,H,W]."""
+                    save_keys=None, cond_only=False, token_idx=None, capture_b0=None, controlnet=None, control=None):
+        """sample [B,4,H,W] fp16 (B even), t_dev float32 [B] on device, ctx [B,T,768] fp16 -> eps [B,4,H,W].
+
+        ControlNet residuals arrive either as NCHW tensors (down_residuals / mid_residual: the reference call
+        surface, ip_adapter/unet_2d_condition.py:1044-1053, 1077-1078) or fused: `controlnet` (a TGControlNet) with
+        `control = dict(rows=(r0, r1), ctx=[r1-r0,77,768], cond_emb=...)` runs the ControlNet encoder on batch rows
+        [r0, r1) of this very forward and its zero-convolutions add straight into the skip tensors (GEMM epilogue).
+        capture_b0: first batch row whose text-attention probabilities are captured (default B/2 when cond_only)."""
         w = self.w
         B, _, H, W = sample.shape
         assert B % 2 == 0, "co-batched CFG pairs: batch must be even"
@@ -269,37 +326,25 @@ class TGUNet:
         n_text = T - n_ip
         if n_ip and ip_scale is None:
             ip_scale = self._ip_scale_tensor(B)
-        emb = ops.timestep_embedding(t_dev, 320)
-        emb = ops.gemm(emb, w["t1.w"], w["t1.b"], act=ops.TG_ACT_SILU)
-        emb = ops.gemm(emb, w["t2.w"], w["t2.b"], act=ops.TG_ACT_SILU)  # = silu(time_embedding(t)), its only use
-        temb_all = ops.gemm(emb, w["temb.w"], w["temb.b"])
-        ctxkv = ops.gemm(ctx.reshape(B * T, -1), w["ctxkv.w"])
+        temb_all, ctxkv = self._time_and_context(t_dev, ctx, B)
 
         def tf(p, x, h_, w_):
             return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
-                                     token_idx)
+                                     token_idx, capture_b0)
 
         x = ops.conv_in(sample, w["conv_in.w"], w["conv_in.b"])
-        skips = [x]
-        h_, w_ = H, W
-        for i in range(4):
-            for j in range(2):
-                x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all, B, h_, w_)
-                if i < 3:
-                    x = tf(f"down_blocks.{i}.attentions.{j}", x, h_, w_)
-                skips.append(x)
-            if i < 3:
-                c = BLOCK_OUT[i]
-                x = ops.gemm(ops.im2col_s2(x), w[f"down{i}.w"], w[f"down{i}.b"]).view(B, h_ // 2, w_ // 2, c)
-                h_, w_ = h_ // 2, w_ // 2
-                skips.append(x)
+        x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
+        ctrl = None
+        if controlnet is not None:
+            r0, r1 = control["rows"]
+            ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
         if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
             skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
-        x = self._resnet("mid_block.resnets.0", x, None, temb_all, B, h_, w_)
-        x = tf("mid_block.attentions.0", x, h_, w_)
-        x = self._resnet("mid_block.resnets.1", x, None, temb_all, B, h_, w_)
+        x = self._mid(x, temb_all, tf, B, h_, w_)
         if mid_residual is not None:
             x = ops.add_inplace(x, ops.nchw_to_nhwc(mid_residual))
+        if ctrl is not None:  # after the mid block: the last skip tensor is also the mid block's input
+            controlnet.add_residuals_inplace(ctrl, skips, x, r0, r1)
         for i in range(4):
             for j in range(3):
                 x = self._resnet(f"up_blocks.{i}.resnets.{j}", x, skips.pop(), temb_all, B, h_, w_)
