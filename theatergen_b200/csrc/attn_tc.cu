@@ -1,14 +1,21 @@
-// tcgen05 flash self-attention for head dims <= 64 (SD-1.5's 64x64 level: N = 4096, d = 40 -- 90 % of the
-// self-attention time).  Q/K/V arrive head-padded to 64 columns (zero weight rows in the fused QKV projection), so
-// every operand tile is the canonical 128-byte-row SWIZZLE_128B layout that TMA writes and tcgen05.mma reads.
+// tcgen05 flash self-attention for head dims <= 56 (SD-1.5's 64x64 level: N = 4096, d = 40 -- 90 % of the
+// self-attention time).  K/V arrive head-padded to 64 columns (zero weight rows in the fused QKV projection), so
+// every K/V tile is the canonical 128-byte-row SWIZZLE_128B layout that TMA writes and tcgen05.mma reads.
 //
-// Per CTA: one (batch, head, 128-query tile); KV tiles of 64 keys stream through a 3-stage TMA ring.
-//   warp 0      TMA producer (Q once, then K_j | V_j per stage)
-//   warp 1      TMEM allocator + single-thread MMA issuer:
-//                   S_j = Q K_j^T           (M=128, N=64, K=ceil(d/16)*16)   -> TMEM S[j&1]
-//                   O_j = P_j V_j           (M=128, N=64, K=64; V is the MN-major B operand) -> TMEM O[j&1]
-//   warps 2..5  one query row per thread (row == TMEM lane): softmax numerators in registers, P_j -> fp16 ->
-//               swizzled smem (the A operand of the second MMA).
+// Per CTA: one (batch, head, 128-query tile); keys stream through a 3-stage TMA ring, 128 keys (two 64-key score
+// tiles) per stage -- a group of TMA loads issued after a barrier wait costs ~570 cycles whatever its size (measured,
+// tools/probes), so a stage carries two tiles.
+//   warp 0      TMA producer (K_2s..2s+1 | V_2s..2s+1 per stage: two 16 KB boxes)
+//   warp 1      TMEM allocator + single-thread MMA issuer, BOTH products with the A operand in TENSOR MEMORY (.ts form):
+//                   S_j = Q K_j^T      (A = Q in TMEM, M=128, N=64, K=ceil(d/16)*16)               -> TMEM S[j&1]
+//                   O  += P_j V_j      (A = P_j in TMEM, M=128, N=64; V is the MN-major B operand)  -> TMEM O
+//               Measured on B200: a 128 x N x 16 MMA with N <= 64 takes 88 cycles with A in shared memory (bound by the
+//               4 KB A read) but 45 cycles with A in tensor memory.
+//   warps 2..5  one query row per thread (row == TMEM lane): Q row -> TMEM once; per tile S_j -> registers, softmax
+//               numerators, P_j -> fp16 pairs -> tcgen05.st INTO THE COLUMNS OF S_j (P overlays S: the tensor pipe executes
+//               in issue order, so S_{j+2} cannot overwrite P_j before P_j V_j has read it -- no extra barrier).
+//               (Measured: splitting a row's 64 columns over two warps -- 8 softmax warps, row max exchanged through
+//               shared memory -- is 8 % slower: the tile is paced by TMEM->register bandwidth, not by warp latency.)
 // What bounds this kernel is TMEM->register bandwidth and the MUFU pipe, so the design minimises both:
 //   * O is accumulated IN TMEM across all KV tiles (accumulate flag) and is read exactly once, at the end.
 //     The running max is only a reference exponent: it is raised -- and O rescaled in TMEM (tcgen05.ld / st)
@@ -17,7 +24,7 @@
 //   * the softmax denominator is not summed by CUDA cores: column d of each V tile is set to 1.0 in shared
 //     memory, so the tensor core accumulates sum_k P[k] in O[:, d] with exactly the same rescaling as O.
 // S is double-buffered in TMEM so the tensor core computes S_{j+1} while the softmax warps work on S_j; two CTAs
-// fit per SM (96 KB smem, 256 TMEM columns each).  The N x N probabilities never leave the SM
+// fit per SM (97 KB smem, 256 TMEM columns each).  The N x N probabilities never leave the SM
 // (reference: AttnProcessor.__call__, ip_adapter/attention_processor.py:343-356, materialises them in HBM).
 #include "common.cuh"
 #include "ops.h"
@@ -25,17 +32,19 @@
 namespace tg {
 
 static constexpr int ATQ = 128;   // queries per CTA
-static constexpr int ATK = 64;    // keys per tile
+static constexpr int ATK = 64;    // keys per score tile
 static constexpr int ATD = 64;    // padded head dim
+static constexpr int AT_TPS = 2;  // score tiles per pipeline stage
 static constexpr int AT_STAGES = 3;
-static constexpr int AT_Q_BYTES = ATQ * ATD * 2;        // 16 KB
-static constexpr int AT_KV_BYTES = ATK * ATD * 2;       // 8 KB each
-static constexpr int AT_STAGE_BYTES = 2 * AT_KV_BYTES;  // K | V
-static constexpr int AT_P_OFFSET = AT_Q_BYTES + AT_STAGES * AT_STAGE_BYTES;
-static constexpr int AT_P_BYTES = ATQ * ATK * 2;        // 16 KB, double-buffered
-static constexpr int AT_BAR_OFFSET = AT_P_OFFSET + 2 * AT_P_BYTES;
-static constexpr int AT_NUM_BARS = 1 + 2 * AT_STAGES + 2 + 2 + 2 + 2 + 2;  // q, kv full/empty, s f/e, o f/e, p f/e
+static constexpr int AT_KV_BYTES = AT_TPS * ATK * ATD * 2;  // 16 KB: 128 keys of K (or V)
+static constexpr int AT_STAGE_BYTES = 2 * AT_KV_BYTES;      // K | V
+static constexpr int AT_SOFTMAX_WARPS = 4;
+static constexpr int AT_THREADS = 64 + AT_SOFTMAX_WARPS * 32;
+static constexpr int AT_BAR_OFFSET = AT_STAGES * AT_STAGE_BYTES;
+static constexpr int AT_NUM_BARS = 2 * AT_STAGES + 2 + 2 + 2;  // kv full/empty, s_full, p_full, o_full
 static constexpr int AT_SMEM = AT_BAR_OFFSET + AT_NUM_BARS * 8 + 16 + 1024;
+// tensor memory columns (256 per CTA): S0 | S1 (P_j overlays the first 32 columns of S_j) | O | Q
+static constexpr uint32_t AT_TS = 0, AT_TO = 128, AT_TQ = 192;
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -61,47 +70,72 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t saddr) {
   return d;
 }
 
-__global__ void __launch_bounds__(192, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+// D[tmem] (+)= A[tmem] * B[smem]^T ; kind::f16, A operand in tensor memory (lane = row, 32-bit column c = elements 2c, 2c+1)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, __half* __restrict__ O, int ldo, int N, int d,
                float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sKV = smem + AT_Q_BYTES;
-  uint8_t* sP = smem + AT_P_OFFSET;
+  uint8_t* sKV = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAR_OFFSET);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_full = bars;
   uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES;
-  uint64_t* s_empty = s_full + 2;
-  uint64_t* o_full = s_empty + 2;
-  uint64_t* o_empty = o_full + 2;
-  uint64_t* p_full = o_empty + 2;  // [2]: P is double-buffered; its reuse is ordered by o_full (P.V of tile j-2 retired)
+  uint64_t* s_full = kv_empty + AT_STAGES;  // [2] S_j complete in TMEM
+  uint64_t* p_full = s_full + 2;            // [2] P_j (and the ones column of V_j) written by the 4 softmax warps
+  uint64_t* o_full = p_full + 2;            // [2] P_j V_j retired (lazy rescale / final read of O)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + AT_NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ATQ;
-  const int T = N / ATK;
+  const int T = N / ATK;             // score tiles
+  const int NS = T / AT_TPS;         // pipeline stages' worth of keys (N is a multiple of 128)
   const int row_base = b * N;
+  const int ksteps = (d + 15) / 16;  // K extent of Q K^T in MMA steps (Q columns >= d are zero)
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
     for (int s = 0; s < AT_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 4);
-      mbar_init(&o_full[s], 1);  // pv_done[s]: P.V of a tile using P buffer s has retired
+      mbar_init(&p_full[s], AT_SOFTMAX_WARPS);
+      mbar_init(&o_full[s], 1);
     }
-    mbar_init(&p_full[0], 4);
-    mbar_init(&p_full[1], 4);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -114,65 +148,76 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   grid_dep_launch();  // PDL: the prologue above overlapped the previous kernel's tail
   grid_dep_wait();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;  // S[2] at +0,+64 ; O (single, accumulated) at +128
+  const uint32_t tS = tmem_base + AT_TS, tO = tmem_base + AT_TO, tQ = tmem_base + AT_TQ;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, h * ATD, row_base + q0);
-      for (int j = 0; j < T; ++j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+      for (int i = 0; i < NS; ++i) {
+        const int s = i % AT_STAGES;
+        mbar_wait(&kv_empty[s], ((i / AT_STAGES) & 1) ^ 1);
         uint8_t* dst = sKV + s * AT_STAGE_BYTES;
         mbar_arrive_expect_tx(&kv_full[s], AT_STAGE_BYTES);
-        tma_load_2d(dst, &tmK, &kv_full[s], h * ATD, row_base + j * ATK);
-        tma_load_2d(dst + AT_KV_BYTES, &tmV, &kv_full[s], h * ATD, row_base + j * ATK);
+        tma_load_2d(dst, &tmK, &kv_full[s], h * ATD, row_base + i * AT_TPS * ATK);
+        tma_load_2d(dst + AT_KV_BYTES, &tmV, &kv_full[s], h * ATD, row_base + i * AT_TPS * ATK);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_f16(ATQ, ATK);                     // A, B K-major
+      constexpr uint32_t idesc_s = make_idesc_f16(ATQ, ATK);                     // B (= K tile) K-major
       // P.V: N = d + 1 (the ones column) rounded up to 16; B (= V) is MN-major
       const uint32_t idesc_o = make_idesc_f16(ATQ, ((d + 1 + 15) / 16) * 16) | (1u << 16);
-      const int ksteps = (d + 15) / 16;
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       auto issue_s = [&](int j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
-        mbar_wait(&s_empty[j & 1], ((j >> 1) & 1) ^ 1);
+        const int i = j / AT_TPS, s = i % AT_STAGES;
+        if (j % AT_TPS == 0) mbar_wait(&kv_full[s], (i / AT_STAGES) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + s * AT_STAGE_BYTES);
+        // S buffer j&1 held S_{j-2} / P_{j-2}: the softmax warps are done with it (p_full[j-2] was waited before
+        // P_{j-2} V_{j-2} was issued) and the tensor pipe runs in issue order, so P_{j-2} V_{j-2} reads P before this
+        // MMA overwrites it
+        const uint32_t k_addr = smem_u32(sKV + s * AT_STAGE_BYTES + (j % AT_TPS) * (ATK * ATD * 2));
         for (int k = 0; k < ksteps; ++k)
-          umma_f16_ss(tS + (j & 1) * 64, make_smem_desc_sw128(q_addr + k * 32), make_smem_desc_sw128(k_addr + k * 32),
-                      idesc_s, k > 0 ? 1u : 0u);
+          umma_f16_ts(tS + (j & 1) * 64, tQ + k * 8, make_smem_desc_sw128(k_addr + k * 32), idesc_s, k > 0 ? 1u : 0u);
         tc_commit(&s_full[j & 1]);
       };
-      mbar_wait(q_full, 0);
+      mbar_wait(&p_full[0], 0);  // phase 0 of p_full[0]: the Q rows are in tensor memory (see the softmax warps)
       issue_s(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_s(j + 1);
-        const int s = j % AT_STAGES;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        const int i = j / AT_TPS, s = i % AT_STAGES;
+        mbar_wait(&p_full[j & 1], ((j >> 1) & 1) ^ (j & 1 ? 0 : 1));  // buffer 0 spent one extra phase on Q
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_BYTES);
-        const uint32_t pj_addr = p_addr + (j & 1) * AT_P_BYTES;
+        const uint32_t v_addr = smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_BYTES + (j % AT_TPS) * (ATK * ATD * 2));
 #pragma unroll
         for (int k = 0; k < ATK / 16; ++k)
-          umma_f16_ss(tO, make_smem_desc_sw128(pj_addr + k * 32), make_smem_desc_sw128_mn(v_addr + k * 2048), idesc_o,
+          umma_f16_ts(tO, tS + (j & 1) * 64 + k * 8, make_smem_desc_sw128_mn(v_addr + k * 2048), idesc_o,
                       (j > 0 || k > 0) ? 1u : 0u);  // O accumulates in TMEM over all tiles
         tc_commit(&o_full[j & 1]);
-        tc_commit(&kv_empty[s]);
+        if (j % AT_TPS == AT_TPS - 1) tc_commit(&kv_empty[s]);
       }
     }
   } else {
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // query row inside the tile == TMEM lane
-    const int tid_s = threadIdx.x - 64;  // 0..127 among the softmax threads
+    const int q = warp & 3;               // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+    const int r = q * 32 + lane;          // query row inside the tile == TMEM lane
+    const int tid_s = threadIdx.x - 64;   // 0..127 among the softmax threads
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int nacc = ((d + 1 + 15) / 16) * 16;  // accumulator columns in use: d outputs + the denominator
     float m_ref = -INFINITY;  // reference exponent (a stale running max is fine: P <= 2^8)
     // position of element (key k, column d) inside a swizzled V tile: 16-byte chunk (d/8) ^ (k & 7)
     const int ones_off = (tid_s & 63) * 128 + ((((d >> 3) ^ (tid_s & 7)) << 4) | ((d & 7) << 1));
+
+    // Q row -> tensor memory (A operand of every S MMA): 16 fp16 = 8 packed columns per MMA K-step
+    {
+      const uint4* qrow = reinterpret_cast<const uint4*>(Q + (size_t)(row_base + q0 + r) * ldq + h * ATD);
+      for (int k = 0; k < ksteps; ++k) {
+        uint4 v[2];
+        v[0] = __ldg(qrow + 2 * k);
+        v[1] = __ldg(qrow + 2 * k + 1);
+        tmem_st_32x32b_x8(tQ + k * 8 + lane_off, reinterpret_cast<const uint32_t*>(v));
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[0]);
+    }
 
     for (int j = 0; j < T; ++j) {
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
@@ -186,17 +231,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sr[i] = t0[i]; sr[32 + i] = t1[i]; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[j & 1]);  // S buffer may be overwritten by tile j+2
 
-      // the ones column of this stage's V tile (its TMA landed before S_j was issued); 64 threads, one store each
+      // the ones column of this tile's V (its TMA landed before S_j was issued); 64 threads, one store each
       if (tid_s < 64)
-        *reinterpret_cast<__half*>(sKV + (j % AT_STAGES) * AT_STAGE_BYTES + AT_KV_BYTES + ones_off) = __float2half(1.f);
+        *reinterpret_cast<__half*>(sKV + ((j / AT_TPS) % AT_STAGES) * AT_STAGE_BYTES + AT_KV_BYTES +
+                                   (j % AT_TPS) * (ATK * ATD * 2) + ones_off) = __float2half(1.f);
 
-      float mx = -INFINITY;
+      // row max: four independent chains instead of one 64-deep dependent chain
+      float m4[4];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      for (int i = 0; i < 4; ++i) m4[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int i = 4; i < 64; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sr[i]));
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       if (j == 0) {
         m_ref = mx;  // O is still empty (the first P.V overwrites it)
       } else {
@@ -216,32 +263,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tmem_st_32x32b_x32(tO + c + lane_off, t);
           }
           tmem_st_wait();
-          tc_fence_before();
         }
       }
       const float msc = m_ref * scale_log2;
 
-      // P buffer j&1 was last read by P.V of tile j-2
-      mbar_wait(&o_full[j & 1], ((j >> 1) & 1) ^ 1);
-      uint8_t* p_row = sP + (j & 1) * AT_P_BYTES + r * 128;
+      uint32_t pk[32];  // P row: 64 fp16 numerators, two per 32-bit tensor-memory column
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {  // 8 keys -> one 16-byte chunk of the swizzled P row
-        uint32_t pk[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float x0 = __uint_as_float(sr[8 * i + 2 * k]) * scale_log2 - msc;
-          const float x1 = __uint_as_float(sr[8 * i + 2 * k + 1]) * scale_log2 - msc;
-          // fp32 exp2 (one MUFU each -- ex2.f16x2 is split into two MUFU ops on sm_100 anyway, and with a stale
-          // reference exponent the dominant terms sit at |x| up to 8 where an fp16 argument would cost 0.3 %)
-          float p0, p1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
-          const __half2 hp = __floats2half2_rn(p0, p1);
-          pk[k] = *reinterpret_cast<const uint32_t*>(&hp);
-        }
-        *reinterpret_cast<uint4*>(p_row + ((i ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      for (int i = 0; i < 32; ++i) {
+        const float x0 = __uint_as_float(sr[2 * i]) * scale_log2 - msc;
+        const float x1 = __uint_as_float(sr[2 * i + 1]) * scale_log2 - msc;
+        // fp32 exp2 (one MUFU each -- ex2.f16x2 is split into two MUFU ops on sm_100 anyway, and with a stale
+        // reference exponent the dominant terms sit at |x| up to 8 where an fp16 argument would cost 0.3 %)
+        float p0, p1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+        const __half2 hp = __floats2half2_rn(p0, p1);
+        pk[i] = *reinterpret_cast<const uint32_t*>(&hp);
       }
-      fence_proxy_async();
+      tmem_st_32x32b_x32(tS + (j & 1) * 64 + lane_off, pk);  // P_j overlays the first half of S_j
+      tmem_st_wait();
+      fence_proxy_async();  // the ones column (generic-proxy smem store) -> visible to the tensor core
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
@@ -296,12 +338,12 @@ int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int
     TG_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr = true;
   }
-  CUtensorMap tq, tk, tv;
+  TG_CHECK(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0, "attention_tc: Q must be 16-byte aligned with a pitch multiple of 8");
+  CUtensorMap tk, tv;
   const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * ATD;
-  if (make_tmap_2d(&tq, Q, rows, cols, ldq, ATQ)) return -1;
-  if (make_tmap_2d(&tk, K, rows, cols, ldk, ATK)) return -1;
-  if (make_tmap_2d(&tv, V, rows, cols, ldv, ATK)) return -1;
-  TG_CUDA(launch_kernel(attn_tc_kernel, dim3(N / ATQ, heads, B), dim3(192), AT_SMEM, st, 1, tq, tk, tv, O, ldo, N, d,
+  if (make_tmap_2d(&tk, K, rows, cols, ldk, AT_TPS * ATK)) return -1;
+  if (make_tmap_2d(&tv, V, rows, cols, ldv, AT_TPS * ATK)) return -1;
+  TG_CUDA(launch_kernel(attn_tc_kernel, dim3(N / ATQ, heads, B), dim3(AT_THREADS), AT_SMEM, st, 1, Q, ldq, tk, tv, O, ldo, N, d,
                         scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
   return 0;

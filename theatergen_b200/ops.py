@@ -32,7 +32,8 @@ class profile:
 
     def finish(self):
         torch.cuda.synchronize()
-        self.rows = [(k, s.elapsed_time(e), f, b) for k, s, e, f, b in self.events]
+        self.rows = [(k, s.elapsed_time(e), f, b) for k, s, e, f, b, _ in self.events]
+        self.tagged = [(k, t, s.elapsed_time(e), f, b) for k, s, e, f, b, t in self.events]
         return self.rows
 
     def summary(self):
@@ -45,7 +46,7 @@ class profile:
                 for k, v in agg.items()}
 
 
-def _timed(kernel, flops, nbytes, fn):
+def _timed(kernel, flops, nbytes, fn, tag=""):
     if _PROF is None:
         return fn()
     st = torch.cuda.current_stream()
@@ -53,7 +54,7 @@ def _timed(kernel, flops, nbytes, fn):
     s.record(st)
     r = fn()
     e.record(st)
-    _PROF.events.append((kernel, s, e, float(flops), float(nbytes)))
+    _PROF.events.append((kernel, s, e, float(flops), float(nbytes), tag))
     return r
 
 
@@ -88,7 +89,7 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
                 lambda: _lib.lib().tg_gemm(_p(a), a.stride(0), K1, _p(a2), 0 if a2 is None else a2.stride(0), _p(w), M, N, K,
                             _p(bias), _p(rowbias), rows_per_image, 0 if rowbias is None else rowbias.stride(0),
                             _p(residual), 0 if residual is None else residual.stride(0), act, float(out_scale),
-                            _p(out), out.stride(0), _stream()))
+                            _p(out), out.stride(0), _stream()), tag=f"lin M={M} N={N} K={K} act={act}")
     _lib.check(rc, "tg_gemm")
     return out
 
@@ -107,7 +108,8 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, ou
                 2.0 * (Mc * Cin + Cout * 9 * Cin + Mc * Cout + (Mc * Cout if res2 is not None else 0)),
                 lambda: _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
                                0 if rowbias is None else rowbias.stride(0), _p(res2),
-                               0 if res2 is None else res2.stride(0), act, float(out_scale), _p(out), Cout, _stream()))
+                               0 if res2 is None else res2.stride(0), act, float(out_scale), _p(out), Cout, _stream()),
+                tag=f"conv M={Mc} N={Cout} K={9 * Cin}")
     _lib.check(rc, "tg_conv3x3")
     return out
 
@@ -136,7 +138,7 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=False, out=None, workspace=
     ws = workspace if workspace is not None else _gn_workspace(x1.device, B)
     rc = _timed("groupnorm", 0, 2.0 * 3 * B * HW * (C1 + C2),
                 lambda: _lib.lib().tg_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, _p(gamma), _p(beta), float(eps), int(silu),
-                                                _p(out), _p(ws), _stream()))
+                                                _p(out), _p(ws), _stream()), tag=f"gn B={B} HW={HW} C={C1 + C2}")
     _lib.check(rc, "tg_groupnorm")
     return out
 

@@ -22,6 +22,45 @@ __device__ __forceinline__ void csync() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(d), "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+
+// TS mode: A (128 x 64 fp16 = 32 TMEM columns) lives in tensor memory, B in shared memory
+__global__ void __launch_bounds__(128, 1) probe_ts(int N, int iters, int b_mn_major, long long* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256 * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 1 && lane == 0) {
+    uint32_t idesc = make_idesc_f16(128, N);
+    if (b_mn_major) idesc |= 1u << 16;
+    const uint32_t b = smem_u32(smem);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ts(tmem + (it & 1) * 128, tmem + 256 + k * 8, make_smem_desc_sw128(b + (b_mn_major ? k * 2048 : k * 32)), idesc, 1);
+    }
+    tc_commit(&bar);
+    mbar_wait(&bar, 0);
+    if (blockIdx.x == 0) out[1] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 // iters k-blocks of 4 MMAs (K = 64 per k-block), rotating over `stages` resident smem stages
 template <bool PAIR>
 __global__ void __launch_bounds__(128, 1) probe(int N, int iters, int stages, long long* out) {
@@ -114,5 +153,15 @@ int main() {
   }
   run<false>(256, iters, 1, 148, d_out);
   run<true>(256, iters, 1, 148, d_out);
+  for (int N : {48, 64, 128, 256}) run<false>(N, iters, 4, 148, d_out);
+  cudaFuncSetAttribute(probe_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int mn = 0; mn < 2; ++mn) for (int N : {16, 48, 64, 128, 256}) {
+    if (mn && N > 64) continue;
+    probe_ts<<<148, 128, 40 * 1024>>>(N, iters, mn, d_out);
+    probe_ts<<<148, 128, 40 * 1024>>>(N, iters, mn, d_out);
+    cudaError_t err = cudaDeviceSynchronize();
+    long long h[2]; cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("TS (A in TMEM) M=128 N=%3d B %s : %7.1f clk/MMA  %s\n", N, mn ? "MN-major" : "K-major ", h[1] / (4.0 * iters), err == cudaSuccess ? "" : cudaGetErrorString(err));
+  }
   return 0;
 }
