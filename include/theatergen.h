@@ -68,6 +68,12 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream);
 
+/* tg_gemm / tg_conv3x3 keep a split-K workspace (fp32 partials + arrival counters) per device and SLOT.  Launches that
+ * may run concurrently on different streams must use different slots (0..3); the slot is a property of the calling
+ * host thread and applies to the launches it enqueues afterwards.  Default slot 0.  (No reference counterpart: the
+ * reference runs everything on one stream.) */
+int tg_gemm_set_scratch_slot(int slot);
+
 /* Measurement hook (no reference counterpart): with a non-NULL device buffer of >= 8*grid int64, every tg_gemm /
  * tg_conv3x3 CTA records {main-loop cycles, producer wait, MMA wait on data, MMA wait on accumulator, epilogue wait,
  * k-blocks, tiles} so a run can tell which role of the pipeline the others wait for.  NULL switches it off. */

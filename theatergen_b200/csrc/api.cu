@@ -43,6 +43,8 @@ int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, in
   return tg::groupnorm_nhwc(H(x1), C1, H(x2), C2, B, HW, H(gamma), H(beta), eps, silu, HM(out), workspace, ST(stream));
 }
 
+int tg_gemm_set_scratch_slot(int slot) { return tg::gemm_set_scratch_slot(slot); }
+
 int tg_gemm_set_prof(void* dev_buf) {
   tg::gemm_set_prof(static_cast<long long*>(dev_buf));
   return 0;

@@ -595,15 +595,25 @@ struct DeviceScratch {
   int* sem = nullptr;
   int num_sms = 0;
 };
-static DeviceScratch g_scratch[16];
+// Split-K workspace (partials + per-tile arrival counters) per (device, slot).  GEMMs enqueued on different streams may
+// run concurrently (the stage-2 ControlNet encoder runs beside the UNet encoder) and must not share semaphores: the
+// caller selects a slot per stream with gemm_set_scratch_slot (slot 0 unless told otherwise).
+static constexpr int MAX_SLOTS = 4;
+static DeviceScratch g_scratch[16][MAX_SLOTS];
+static thread_local int g_slot = 0;
+int gemm_set_scratch_slot(int slot) {
+  TG_CHECK(slot >= 0 && slot < MAX_SLOTS, "scratch slot %d out of range [0,%d)", slot, MAX_SLOTS);
+  g_slot = slot;
+  return 0;
+}
 
 static int get_scratch(DeviceScratch** out) {
   int dev = 0;
   TG_CUDA(cudaGetDevice(&dev));
   TG_CHECK(dev >= 0 && dev < 16, "device index %d out of range", dev);
-  DeviceScratch& s = g_scratch[dev];
+  DeviceScratch& s = g_scratch[dev][g_slot];
   if (s.ws == nullptr) {
-    // allocated once per device, outside any stream capture (every captured path is warmed up eagerly first)
+    // allocated once per (device, slot), outside any stream capture (every captured path is warmed up eagerly first)
     TG_CUDA(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
     TG_CUDA(cudaMalloc(&s.ws, SPLITK_WS_BYTES));
     TG_CUDA(cudaMalloc(&s.sem, SPLITK_MAX_TILES * sizeof(int)));

@@ -26,6 +26,8 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
 
 // allocates the per-device split-K workspace (call once outside stream capture; lazily done otherwise)
 int gemm_init();
+// selects the split-K workspace used by GEMMs enqueued from this host thread (one slot per concurrently running stream)
+int gemm_set_scratch_slot(int slot);
 // measurement hook: when non-null every GEMM CTA writes 8 counters {main-loop cycles, producer wait, MMA wait(full),
 // MMA wait(accumulator), epilogue wait, k-blocks, tiles, -} at dev_buf[blockIdx.x*8..] (tools/gemm_probe.py)
 void gemm_set_prof(long long* dev_buf);

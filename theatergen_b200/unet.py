@@ -12,9 +12,11 @@ The wiring follows ip_adapter/unet_2d_condition.py:799-1125 and the block files 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
-from . import ops
+from . import _lib, ops
 from .weights import pack_conv3x3, pack_geglu
 
 BLOCK_OUT = (320, 640, 1280, 1280)
@@ -298,6 +300,11 @@ class TGUNet(_BlockNet):
         return 2 * n
 
     # -------------------------------------------------------------------------------------------------
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _ip_scale_tensor(self, B):
         if self.ip_scale_per_sample is not None:
             assert self.ip_scale_per_sample.numel() == B
@@ -332,18 +339,33 @@ class TGUNet(_BlockNet):
             return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
                                      token_idx, capture_b0)
 
+        ctrl = side = None
+        if controlnet is not None:
+            # The ControlNet encoder (batch r1-r0, small grids) runs on a side stream beside the UNet encoder: fork here,
+            # join before its residuals are added.  Under CUDA-graph capture the two become parallel graph branches.
+            r0, r1 = control["rows"]
+            if os.environ.get("TG_CN_OVERLAP", "1") == "0":  # A/B measurements: ControlNet in line on the main stream
+                ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
+            else:
+                main = torch.cuda.current_stream()
+                side = self._side_stream()
+                side.wait_stream(main)
+                _lib.check(_lib.lib().tg_gemm_set_scratch_slot(1), "tg_gemm_set_scratch_slot")  # own split-K workspace
+                try:
+                    with torch.cuda.stream(side):
+                        ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
+                finally:
+                    _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
         x = ops.conv_in(sample, w["conv_in.w"], w["conv_in.b"])
         x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
-        ctrl = None
-        if controlnet is not None:
-            r0, r1 = control["rows"]
-            ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
         if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
             skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
         x = self._mid(x, temb_all, tf, B, h_, w_)
         if mid_residual is not None:
             x = ops.add_inplace(x, ops.nchw_to_nhwc(mid_residual))
         if ctrl is not None:  # after the mid block: the last skip tensor is also the mid block's input
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
             controlnet.add_residuals_inplace(ctrl, skips, x, r0, r1)
         for i in range(4):
             for j in range(3):
