@@ -24,7 +24,7 @@ static constexpr int GN_MAX_BATCH = 256;
 // tunables (tools/gn_bench.py sweeps them through tg_groupnorm_tune): slabs per image of the statistics kernel (a
 // function of the tensor shape only -- never of the batch -- so an image's statistics are summed in the same order
 // whatever batch it travels in), CTAs per SM of the apply kernel, and whether the single-kernel cluster path may be used
-static int g_gn_stats_slabs = GN_MAX_SLABS, g_gn_apply_per_sm = 8, g_gn_fused = 1;
+static int g_gn_stats_slabs = 32, g_gn_apply_per_sm = 8, g_gn_fused = 1;  // measured best (tools/gn_bench.py, B=10)
 void groupnorm_tune(int stats_slabs, int apply_per_sm, int fused) {
   if (stats_slabs > 0) g_gn_stats_slabs = stats_slabs < GN_MAX_SLABS ? stats_slabs : GN_MAX_SLABS;
   if (apply_per_sm > 0) g_gn_apply_per_sm = apply_per_sm;
@@ -139,8 +139,9 @@ __device__ __forceinline__ uint4 gn_emit(const uint4& v, const float (&sa)[8], c
 // single-kernel path: one cluster of GN_FUSED_CLUSTER CTAs per image.  Each CTA streams its slab of rows ONCE from
 // global memory into shared memory while accumulating the statistics, the eight CTAs exchange their 32 x (sum, sumsq)
 // through distributed shared memory, and the slab is normalised (+SiLU) straight out of shared memory: one HBM read, one
-// HBM write, one launch.  Used whenever a slab (HW/8 rows x C) fits on chip (all 8x8 / 16x16 tensors and the 640-channel
-// 32x32 ones).  The cluster size is a function of the tensor shape only, so an image's result does not depend on the
+// HBM write, one launch.  Possible whenever a slab (HW/8 rows x C) fits on chip (all 8x8 / 16x16 tensors and the
+// 640-channel 32x32 ones); used by default at the 8x8 level only, where it measured faster than the two launches of the
+// two-pass path.  The cluster size is a function of the tensor shape only, so an image's result does not depend on the
 // batch it travels in.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_FUSED_THREADS, 1)
@@ -310,7 +311,9 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
     attr = true;
   }
   // ---- single-kernel cluster path ----
-  if (g_gn_fused && HW % GN_FUSED_CLUSTER == 0) {
+  // g_gn_fused: 1 = where it measured faster than the two-pass kernels (the 8x8 level: a cluster launch costs more than
+  // a plain one, which only pays off when it replaces two launches over a tiny tensor), 2 = wherever a slab fits on chip
+  if (g_gn_fused && HW % GN_FUSED_CLUSTER == 0 && (HW <= 64 || g_gn_fused == 2)) {
     const int rows_per = HW / GN_FUSED_CLUSTER;
     const size_t stage = (size_t)rows_per * C * 2;
     const int Rf = GN_FUSED_THREADS / (C / 8);

@@ -45,7 +45,7 @@ def main():
                 ops.groupnorm(xs1[i % 4], gamma, beta, 1e-5, x2=xs2[i % 4], silu=True, out=out)
 
         row = []
-        _lib.lib().tg_groupnorm_tune(64, 8, 1)
+        _lib.lib().tg_groupnorm_tune(64, 8, 2)
         row.append(f"{graph_time(run) / 20 * 1e3:7.1f}")
         for slabs in (16, 32, 64):
             for per_sm in (4, 8, 16):
