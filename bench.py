@@ -337,15 +337,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n, warm):
+    def timed(fn, n, warm, nvtx=None):
         for i in range(warm):
             fn(i)
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if nvtx:  # lets `ncu --nvtx --nvtx-include "<name>/"` list exactly the launches of the timed region
+            torch.cuda.nvtx.range_push(nvtx)
         s.record()
         for i in range(warm, warm + n):
             fn(i)
         e.record()
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
         barrier()
         ms = s.elapsed_time(e)
         if world > 1:
@@ -358,7 +362,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device_mixed if mixed else step_device, Kb, Wb)
+    ms_dev = timed(step_device_mixed if mixed else step_device, Kb, Wb, nvtx="tg_timed")
     clocks = sampler.stop() if rank == 0 else None
     n_energy = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) < 30)
     n_embed = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) == 0)
@@ -388,12 +392,14 @@ def run_ours(args):
     if rank == 0:
         net.ip_scale_per_sample = None
         gp = gme if mixed else g1
+        os.environ["TG_CN_OVERLAP"] = "0"  # per-op timing: no second stream sharing the SMs while an op is timed
         for _ in range(2):
             gp._body()
         with ops.profile() as rec:
             for _ in range(3):
                 gp._body()
         rec.finish()
+        os.environ.pop("TG_CN_OVERLAP", None)
         summ = rec.summary()
         tot = sum(v["ms"] for v in summ.values())
         breakdown = {k: {"launches_per_fwd": v["launches"] // 3, "ms_per_fwd": round(v["ms"] / 3, 4),
@@ -401,8 +407,17 @@ def run_ours(args):
                      for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
         top = max(summ.items(), key=lambda kv: kv[1]["ms"])
         tf_peak, hbm_peak, src = peaks()
+        # DRAM traffic per launch of the same kernel family over the same timed region, from the committed ncu pass
+        # (tools/profile.sh -> profiles/gemm_traffic.json); null when the file is absent
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("mean_dram_bytes_per_launch"), tj.get("source")
         roof = {"kernel": top[0], "bound": "tensor", "achieved": round(top[1]["tflops"], 2), "peak": tf_peak,
-                "unit": "TFLOP/s", "frac": round(top[1]["tflops"] / tf_peak, 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(top[1]["tflops"] / tf_peak, 4), "traffic": traffic,
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": round(top[1]["bytes"] / top[1]["launches"]),
                 "peak_source": f"{src} (bf16_tflops_sustained: kernel timed inside a long step)",
                 "avg_launch_us": round(1e3 * top[1]["ms"] / top[1]["launches"], 2),
                 "algorithmic_flops_per_launch": round(top[1]["flops"] / top[1]["launches"]),
@@ -428,11 +443,11 @@ def run_ours(args):
         burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
         roof["representative_launch"] = {
-            "what": "conv3x3 320->320 @64x64, B=10 (gemm_tc_kernel<160,5>, CONV3 mode), timed alone, 20 launches",
+            "what": "conv3x3 320->320 @64x64, B=10 (gemm_tc_kernel<160,3,pair>, CONV3 mode), timed alone, 20 launches",
             "us": round(us, 2), "achieved": round(fl / us / 1e6, 1), "peak": burst, "unit": "TFLOP/s",
             "frac": round(fl / us / 1e6 / burst, 4), "algorithmic_flops": fl,
             "algorithmic_bytes": 2.0 * (40960 * 320 * 2 + 320 * 2880),
-            "traffic": "see profiles/r01c_full.md (dram__bytes_read+write of the captured launches)"}
+            "traffic": "see profiles/ (dram__bytes_read+write of the captured launches)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

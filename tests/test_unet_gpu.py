@@ -83,3 +83,39 @@ def test_unet_controlnet_residuals_and_odd_batch():
     e2 = net(x.cuda(), 481, encoder_hidden_states=ctx.cuda()).sample
     assert e1.shape == (1, 4, 64, 64)
     assert torch.equal(e1, e2[1:])  # every kernel is deterministic and batch-position independent
+
+
+def test_same_gpu_eager_reference_timing():
+    """Context number for DESIGN.md (not a parity check): the oracle -- the reference's op structure, materialised
+    attention probabilities and all -- executed by PyTorch eager fp16 (cuBLAS / cuDNN) on this same GPU, B=2 and the
+    co-batched B=10, next to TGUNet.  Prints ms per forward; asserts only that our path is not slower."""
+    import time
+    from theatergen_b200.unet import TGUNet
+    OU, sd, _, _ = _setup(2)
+    net = TGUNet(sd)
+    sd16 = {k: v.half().cuda() for k, v in sd.items()}
+    out = {}
+    for B in (2, 10):
+        g = torch.Generator().manual_seed(B)
+        x = torch.randn(B, 4, 64, 64, generator=g).half().cuda()
+        ctx = torch.randn(B, 81, 768, generator=g).half().cuda()
+        t_dev = torch.full((B,), 501.0, device="cuda")
+        sc = torch.full((B,), 0.4, device="cuda")
+
+        def ours():
+            return net.forward_raw(x, t_dev, ctx, ip_scale=sc)
+
+        def ref():
+            with torch.no_grad():
+                return OU.unet_forward(sd16, x, 501, ctx, ip_scale=0.4)
+
+        for name, fn, reps in (("ours_eager", ours, 5), ("torch_eager_fp16", ref, 3)):
+            fn(); fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            out[(name, B)] = (time.perf_counter() - t0) / reps * 1e3
+    print("same-GPU forward time, ms:", {f"{k[0]} B={k[1]}": round(v, 2) for k, v in out.items()})
+    assert out[("ours_eager", 10)] < out[("torch_eager_fp16", 10)]
