@@ -33,15 +33,17 @@ def test_self_attention(B, N, C):
     _close(out, ref, 2e-3, 1e-2, "self-attn")
 
 
-@pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (8, 256, 40), (2, 1024, 48), (1, 128, 8), (2, 512, 32)])
+@pytest.mark.parametrize("B,N,d", [(2, 4096, 40), (8, 256, 40), (2, 1024, 48), (1, 128, 8), (2, 512, 32), (2, 1024, 80),
+                                   (10, 1024, 80), (1, 256, 64), (2, 384, 120), (1, 128, 72)])
 def test_self_attention_tcgen05(B, N, d):
-    """tcgen05/TMEM flash attention on head-padded (64) Q/K/V vs fp32 SDPA."""
+    """tcgen05/TMEM flash attention on head-padded (64 columns for d <= 56, 128 for d <= 120) Q/K/V vs fp32 SDPA."""
     from theatergen_b200 import ops
     heads = 8
-    qkv = torch.zeros((B * N, 3, heads, 64), dtype=torch.float16, device="cuda")
+    pad = 64 if d + 1 <= 64 else 128
+    qkv = torch.zeros((B * N, 3, heads, pad), dtype=torch.float16, device="cuda")
     qkv[..., :d] = _rand((B * N, 3, heads, d), 1, 1.5)
-    flat = qkv.view(B * N, 3 * heads * 64)
-    P = heads * 64
+    flat = qkv.view(B * N, 3 * heads * pad)
+    P = heads * pad
     out = ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d)
     assert out.shape == (B * N, heads * d)
     q, k, v = [qkv[:, i, :, :d].float().reshape(B, N, heads, d).transpose(1, 2) for i in range(3)]

@@ -1,6 +1,8 @@
-// tcgen05 flash self-attention for head dims <= 56 (SD-1.5's 64x64 level: N = 4096, d = 40 -- 90 % of the
-// self-attention time).  K/V arrive head-padded to 64 columns (zero weight rows in the fused QKV projection), so
-// every K/V tile is the canonical 128-byte-row SWIZZLE_128B layout that TMA writes and tcgen05.mma reads.
+// tcgen05 flash self-attention for head dims 8..120 (SD-1.5's 64x64 level: N = 4096, d = 40 -- 90 % of the
+// self-attention time -- and the 32x32 level: N = 1024, d = 80).  Q/K/V arrive head-padded to CH x 64 columns (CH = 1 for
+// d <= 56, 2 for d <= 120; zero weight rows in the fused QKV projection), so every K/V tile is CH canonical 128-byte-row
+// SWIZZLE_128B chunks that TMA writes and tcgen05.mma reads.  CH = 1 runs two CTAs per SM (256 TMEM columns each),
+// CH = 2 one (512 columns, 192 KB of K/V stages).
 //
 // Per CTA: one (batch, head, 128-query tile); keys stream through a 3-stage TMA ring, 128 keys (two 64-key score
 // tiles) per stage -- a group of TMA loads issued after a barrier wait costs ~570 cycles whatever its size (measured,
@@ -33,18 +35,23 @@ namespace tg {
 
 static constexpr int ATQ = 128;   // queries per CTA
 static constexpr int ATK = 64;    // keys per score tile
-static constexpr int ATD = 64;    // padded head dim
+static constexpr int ATD = 64;    // columns of one head chunk
 static constexpr int AT_TPS = 2;  // score tiles per pipeline stage
 static constexpr int AT_STAGES = 3;
-static constexpr int AT_KV_BYTES = AT_TPS * ATK * ATD * 2;  // 16 KB: 128 keys of K (or V)
-static constexpr int AT_STAGE_BYTES = 2 * AT_KV_BYTES;      // K | V
+static constexpr int AT_TILE_BYTES = ATK * ATD * 2;             // 8 KB: 64 keys of one chunk
+static constexpr int AT_CHUNK_BYTES = AT_TPS * AT_TILE_BYTES;   // 16 KB: 128 keys of one chunk of K (or V)
 static constexpr int AT_SOFTMAX_WARPS = 4;
 static constexpr int AT_THREADS = 64 + AT_SOFTMAX_WARPS * 32;
-static constexpr int AT_BAR_OFFSET = AT_STAGES * AT_STAGE_BYTES;
-static constexpr int AT_NUM_BARS = 2 * AT_STAGES + 2 + 2 + 2;  // kv full/empty, s_full, p_full, o_full
-static constexpr int AT_SMEM = AT_BAR_OFFSET + AT_NUM_BARS * 8 + 16 + 1024;
-// tensor memory columns (256 per CTA): S0 | S1 (P_j overlays the first 32 columns of S_j) | O | Q
-static constexpr uint32_t AT_TS = 0, AT_TO = 128, AT_TQ = 192;
+static constexpr int AT_NUM_BARS = 2 * AT_STAGES + 2 + 2 + 2;   // kv full/empty, s_full, p_full, o_full
+template <int CH>
+struct AttnCfg {
+  static constexpr int KV_BYTES = CH * AT_CHUNK_BYTES;          // 128 keys of K (or V), CH chunks
+  static constexpr int STAGE_BYTES = 2 * KV_BYTES;              // K chunks | V chunks
+  static constexpr int BAR_OFFSET = AT_STAGES * STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFFSET + AT_NUM_BARS * 8 + 16 + 1024;
+  // tensor memory columns: S0 | S1 (P_j overlays the first 32 columns of S_j) | O (64 per chunk) | Q (8 per K-step)
+  static constexpr uint32_t TS = 0, TO = 128, TQ = 128 + 64 * CH, TCOLS = CH == 1 ? 256 : 512;
+};
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -102,14 +109,18 @@ __device__ __forceinline__ uint32_t tmem_ld_32x32b_x1(uint32_t taddr) {
   return v;
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+template <int CH>
+__global__ void __launch_bounds__(AT_THREADS, CH == 1 ? 2 : 1)
 attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, __half* __restrict__ O, int ldo, int N, int d,
                float scale_log2) {
+  using Cfg = AttnCfg<CH>;
+  constexpr int AT_KV_BYTES = Cfg::KV_BYTES, AT_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr uint32_t AT_TS = Cfg::TS, AT_TO = Cfg::TO, AT_TQ = Cfg::TQ;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sKV = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_BAR_OFFSET);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
   uint64_t* kv_full = bars;
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;  // [2] S_j complete in TMEM
@@ -139,7 +150,7 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, Cfg::TCOLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -157,15 +168,24 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
         mbar_wait(&kv_empty[s], ((i / AT_STAGES) & 1) ^ 1);
         uint8_t* dst = sKV + s * AT_STAGE_BYTES;
         mbar_arrive_expect_tx(&kv_full[s], AT_STAGE_BYTES);
-        tma_load_2d(dst, &tmK, &kv_full[s], h * ATD, row_base + i * AT_TPS * ATK);
-        tma_load_2d(dst + AT_KV_BYTES, &tmV, &kv_full[s], h * ATD, row_base + i * AT_TPS * ATK);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          tma_load_2d(dst + c * AT_CHUNK_BYTES, &tmK, &kv_full[s], (h * CH + c) * ATD, row_base + i * AT_TPS * ATK);
+          tma_load_2d(dst + AT_KV_BYTES + c * AT_CHUNK_BYTES, &tmV, &kv_full[s], (h * CH + c) * ATD, row_base + i * AT_TPS * ATK);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(ATQ, ATK);                     // B (= K tile) K-major
-      // P.V: N = d + 1 (the ones column) rounded up to 16; B (= V) is MN-major
-      const uint32_t idesc_o = make_idesc_f16(ATQ, ((d + 1 + 15) / 16) * 16) | (1u << 16);
+      // P.V: one MMA per head chunk, N = 64 for full chunks and (d + 1 (the ones column) - 64 c) rounded up to 16 for the
+      // last one; B (= V chunk) is MN-major
+      uint32_t idesc_o[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int nc = (c + 1 < CH) ? 64 : ((d + 1 - 64 * c + 15) / 16) * 16;
+        idesc_o[c] = make_idesc_f16(ATQ, nc) | (1u << 16);
+      }
       auto issue_s = [&](int j) {
         const int i = j / AT_TPS, s = i % AT_STAGES;
         if (j % AT_TPS == 0) mbar_wait(&kv_full[s], (i / AT_STAGES) & 1);
@@ -173,9 +193,10 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
         // S buffer j&1 held S_{j-2} / P_{j-2}: the softmax warps are done with it (p_full[j-2] was waited before
         // P_{j-2} V_{j-2} was issued) and the tensor pipe runs in issue order, so P_{j-2} V_{j-2} reads P before this
         // MMA overwrites it
-        const uint32_t k_addr = smem_u32(sKV + s * AT_STAGE_BYTES + (j % AT_TPS) * (ATK * ATD * 2));
-        for (int k = 0; k < ksteps; ++k)
-          umma_f16_ts(tS + (j & 1) * 64, tQ + k * 8, make_smem_desc_sw128(k_addr + k * 32), idesc_s, k > 0 ? 1u : 0u);
+        const uint32_t k_addr = smem_u32(sKV + s * AT_STAGE_BYTES + (j % AT_TPS) * AT_TILE_BYTES);
+        for (int k = 0; k < ksteps; ++k)  // K-step k: chunk k / 4, 32 bytes per step inside the chunk's 128-byte rows
+          umma_f16_ts(tS + (j & 1) * 64, tQ + k * 8, make_smem_desc_sw128(k_addr + (k >> 2) * AT_CHUNK_BYTES + (k & 3) * 32),
+                      idesc_s, k > 0 ? 1u : 0u);
         tc_commit(&s_full[j & 1]);
       };
       mbar_wait(&p_full[0], 0);  // phase 0 of p_full[0]: the Q rows are in tensor memory (see the softmax warps)
@@ -185,11 +206,13 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
         const int i = j / AT_TPS, s = i % AT_STAGES;
         mbar_wait(&p_full[j & 1], ((j >> 1) & 1) ^ (j & 1 ? 0 : 1));  // buffer 0 spent one extra phase on Q
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_BYTES + (j % AT_TPS) * (ATK * ATD * 2));
+        const uint32_t v_addr = smem_u32(sKV + s * AT_STAGE_BYTES + AT_KV_BYTES + (j % AT_TPS) * AT_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < ATK / 16; ++k)
-          umma_f16_ts(tO, tS + (j & 1) * 64 + k * 8, make_smem_desc_sw128_mn(v_addr + k * 2048), idesc_o,
-                      (j > 0 || k > 0) ? 1u : 0u);  // O accumulates in TMEM over all tiles
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int k = 0; k < ATK / 16; ++k)
+            umma_f16_ts(tO + c * 64, tS + (j & 1) * 64 + k * 8, make_smem_desc_sw128_mn(v_addr + c * AT_CHUNK_BYTES + k * 2048),
+                        idesc_o[c], (j > 0 || k > 0) ? 1u : 0u);  // O accumulates in TMEM over all tiles
         tc_commit(&o_full[j & 1]);
         if (j % AT_TPS == AT_TPS - 1) tc_commit(&kv_empty[s]);
       }
@@ -201,12 +224,14 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const int nacc = ((d + 1 + 15) / 16) * 16;  // accumulator columns in use: d outputs + the denominator
     float m_ref = -INFINITY;  // reference exponent (a stale running max is fine: P <= 2^8)
-    // position of element (key k, column d) inside a swizzled V tile: 16-byte chunk (d/8) ^ (k & 7)
-    const int ones_off = (tid_s & 63) * 128 + ((((d >> 3) ^ (tid_s & 7)) << 4) | ((d & 7) << 1));
+    // position of element (key k, column d) inside the swizzled V tile of head chunk d / 64: 16-byte chunk
+    // ((d % 64) / 8) ^ (k & 7) of row k
+    const int dl = d & 63;
+    const int ones_off = (d >> 6) * AT_CHUNK_BYTES + (tid_s & 63) * 128 + ((((dl >> 3) ^ (tid_s & 7)) << 4) | ((dl & 7) << 1));
 
     // Q row -> tensor memory (A operand of every S MMA): 16 fp16 = 8 packed columns per MMA K-step
     {
-      const uint4* qrow = reinterpret_cast<const uint4*>(Q + (size_t)(row_base + q0 + r) * ldq + h * ATD);
+      const uint4* qrow = reinterpret_cast<const uint4*>(Q + (size_t)(row_base + q0 + r) * ldq + h * CH * ATD);
       for (int k = 0; k < ksteps; ++k) {
         uint4 v[2];
         v[0] = __ldg(qrow + 2 * k);
@@ -235,7 +260,7 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
       // the ones column of this tile's V (its TMA landed before S_j was issued); 64 threads, one store each
       if (tid_s < 64)
         *reinterpret_cast<__half*>(sKV + ((j / AT_TPS) % AT_STAGES) * AT_STAGE_BYTES + AT_KV_BYTES +
-                                   (j % AT_TPS) * (ATK * ATD * 2) + ones_off) = __float2half(1.f);
+                                   (j % AT_TPS) * AT_TILE_BYTES + ones_off) = __float2half(1.f);
 
       // row max: four independent chains instead of one 64-deep dependent chain
       float m4[4];
@@ -287,36 +312,30 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
-    // epilogue: O (and the denominator in column d) is read from TMEM exactly once
+    // epilogue: O (and the denominator in column d) is read from TMEM exactly once, 32 columns at a time
     mbar_wait(&o_full[(T - 1) & 1], ((T - 1) >> 1) & 1);
     tc_fence_after();
-    float acc[ATD];
-    {
-      uint32_t t0[32], t1[32];
-      tmem_ld_32x32b_x32(tO + lane_off, t0);
-      if (nacc > 32) tmem_ld_32x32b_x32(tO + 32 + lane_off, t1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = __uint_as_float(t0[i]);
-        acc[32 + i] = nacc > 32 ? __uint_as_float(t1[i]) : 0.f;
-      }
-    }
-    float l_run = 0.f;
-#pragma unroll
-    for (int i = 0; i < ATD; ++i)
-      if (i == d) l_run = acc[i];
-    const float inv = 1.f / l_run;
+    const uint32_t lden = tmem_ld_32x32b_x1(tO + d + lane_off);
+    tmem_ld_wait();
+    const float inv = 1.f / __uint_as_float(lden);
     __half* orow = O + (size_t)(row_base + q0 + r) * ldo + h * d;
-    const int nvec = d / 8;  // d is a multiple of 8
 #pragma unroll
-    for (int i = 0; i < ATD / 8; ++i) {
-      if (i < nvec) {
-        uint4 o;
-        __half2* hh = reinterpret_cast<__half2*>(&o);
+    for (int c0 = 0; c0 < CH * 64; c0 += 32) {
+      if (c0 < d) {
+        uint32_t t[32];
+        tmem_ld_32x32b_x32(tO + c0 + lane_off, t);
+        tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) hh[k] = __floats2half2_rn(acc[8 * i + 2 * k] * inv, acc[8 * i + 2 * k + 1] * inv);
-        *reinterpret_cast<uint4*>(orow + 8 * i) = o;
+        for (int i = 0; i < 4; ++i) {
+          if (c0 + 8 * i < d) {  // d is a multiple of 8
+            uint4 o;
+            __half2* hh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              hh[k] = __floats2half2_rn(__uint_as_float(t[8 * i + 2 * k]) * inv, __uint_as_float(t[8 * i + 2 * k + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * i) = o;
+          }
+        }
       }
     }
     tc_fence_before();
@@ -325,28 +344,38 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, Cfg::TCOLS);
   }
 }
 
-int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
-                 int B, int heads, int N, int d, float scale, cudaStream_t st) {
-  TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d + 1 <= ATD, "attention_tc: N=%d (multiple of 128) d=%d (<=56, multiple of 8)", N, d);
-  TG_CHECK(ldo % 8 == 0 && (d * 2) % 16 == 0, "attention_tc: output pitch/head offset must be 16B aligned");
+template <int CH>
+static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
+                          int B, int heads, int N, int d, float scale, cudaStream_t st) {
+  using Cfg = AttnCfg<CH>;
+  auto kern = attn_tc_kernel<CH>;
   static bool attr = false;
   if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  TG_CHECK(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0, "attention_tc: Q must be 16-byte aligned with a pitch multiple of 8");
   CUtensorMap tk, tv;
-  const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * ATD;
+  const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * CH * ATD;
   if (make_tmap_2d(&tk, K, rows, cols, ldk, AT_TPS * ATK)) return -1;
   if (make_tmap_2d(&tv, V, rows, cols, ldv, AT_TPS * ATK)) return -1;
-  TG_CUDA(launch_kernel(attn_tc_kernel, dim3(N / ATQ, heads, B), dim3(AT_THREADS), AT_SMEM, st, 1, Q, ldq, tk, tv, O, ldo, N, d,
+  TG_CUDA(launch_kernel(kern, dim3(N / ATQ, heads, B), dim3(AT_THREADS), Cfg::SMEM, st, 1, Q, ldq, tk, tv, O, ldo, N, d,
                         scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
   return 0;
+}
+
+// Q/K/V: [B*N, heads * CH * 64] views (head h at column h * CH * 64, columns >= d zero), CH = 1 for d <= 56, 2 for d <= 120
+int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
+                 int B, int heads, int N, int d, float scale, cudaStream_t st) {
+  TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d >= 8 && d + 1 <= 2 * ATD, "attention_tc: N=%d (multiple of 128) d=%d (8..120, multiple of 8)", N, d);
+  TG_CHECK(ldo % 8 == 0 && (d * 2) % 16 == 0, "attention_tc: output pitch/head offset must be 16B aligned");
+  TG_CHECK(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0, "attention_tc: Q must be 16-byte aligned with a pitch multiple of 8");
+  if (d + 1 <= ATD) return launch_attn_tc<1>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
+  return launch_attn_tc<2>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
 }
 
 }  // namespace tg

@@ -172,7 +172,8 @@ def attention(q, k, v, B, heads, scale=None, out=None):
 
 
 def attention_tc(q, k, v, B, heads, d, scale=None, out=None):
-    """tcgen05 flash attention: q/k/v are [B*N, heads*64] views (head-padded to 64, pad columns zero)."""
+    """tcgen05 flash attention: q/k/v are [B*N, heads*P] views, every head padded with zero columns to P = 64 (d <= 56)
+    or P = 128 (d <= 120)."""
     _chk16(q, k, v, out)
     N = q.shape[0] // B
     if scale is None:

@@ -112,13 +112,16 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip):
     for n in ("norm1", "norm2", "norm3"):
         t[n + "g"], t[n + "b"] = g(f"{tb_}.{n}.weight"), g(f"{tb_}.{n}.bias")
     qkv = [g(f"{tb_}.attn1.to_{x}.weight") for x in "qkv"]
-    t["qkv_pad"] = (c // HEADS) < 64  # d = 40: pad every head to 64 rows (zero weights) for the tcgen05 path
+    # tcgen05 attention path: every head padded (zero weight rows) to 64 columns for d = 40 and to 128 (two 64-column
+    # chunks) for d = 80; d = 160 stays unpadded on the mma.sync kernel
+    d_ = c // HEADS
+    t["qkv_pad"] = 64 if d_ + 1 <= 64 else (128 if d_ + 1 <= 128 else 0)
     if t["qkv_pad"]:
-        d_ = c // HEADS
-        padded = torch.zeros((3, HEADS, 64, c), dtype=torch.float16, device=dev)
+        pad = t["qkv_pad"]
+        padded = torch.zeros((3, HEADS, pad, c), dtype=torch.float16, device=dev)
         for i_, m_ in enumerate(qkv):
             padded[i_, :, :d_] = m_.view(HEADS, d_, c)
-        t["qkvw"] = padded.view(3 * HEADS * 64, c).contiguous()
+        t["qkvw"] = padded.view(3 * HEADS * pad, c).contiguous()
     else:
         t["qkvw"] = torch.cat(qkv, 0).contiguous()
     t["o1w"], t["o1b"] = g(f"{tb_}.attn1.to_out.0.weight"), g(f"{tb_}.attn1.to_out.0.bias")
@@ -199,7 +202,7 @@ class _BlockNet:
         ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
         qkv = ops.gemm(ln, t["qkvw"])
         if t["qkv_pad"] and (H * W) % 128 == 0:
-            P = HEADS * 64
+            P = HEADS * t["qkv_pad"]
             a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], B, HEADS, C // HEADS)
         elif t["qkv_pad"]:
             raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
