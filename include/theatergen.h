@@ -122,6 +122,10 @@ int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, void*
 /* conv_in: NCHW [B,Cin,H,W] (Cin = 4 latents, or 3 for the ControlNet hint image) -> NHWC [B,H,W,Cout], optional SiLU */
 int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_half* y_nhwc, int B, int Cin, int H,
                int W, int Cout, int silu, void* stream);
+/* 3x3 patches of a small-channel NCHW image as GEMM rows: out[B*H*W, 64], column k = ci*9 + ky*3 + kx (a torch
+ * [Cout][Cin][3][3] weight flattened), zero beyond Cin*9.  conv_in (unet_2d_condition.py:999) and the ControlNet hint
+ * embedder's first convolution then run as tg_gemm with K = 64. */
+int tg_im2col_small(const tg_half* x_nchw, tg_half* out, int B, int Cin, int H, int W, void* stream);
 int tg_conv_out(const tg_half* x_nhwc, const tg_half* w, const tg_half* bias, tg_half* y_nchw, int B, int H,
                 int W, int C, void* stream);
 int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream);

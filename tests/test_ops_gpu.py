@@ -201,11 +201,20 @@ def test_conv_in_out():
     out = ops.conv_in(x, w, b)
     ref = F.conv2d(x.float(), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
     _close(out, ref, 2e-3, 2e-3, "conv_in")
+    out_g = ops.conv_in_gemm(x, ops.pack_conv_in(w), b)  # the path TGUNet uses: im2col (K padded to 64) + tcgen05 GEMM
+    _close(out_g, ref, 2e-3, 2e-3, "conv_in_gemm")
+    x3 = _rand((1, 3, 128, 256), 7).abs()  # ControlNet hint embedder: 3 channels, SiLU, non-square
+    w3, b3 = _rand((64, 3, 3, 3), 8, 0.3), _rand((64,), 9, 0.1)
+    out3 = ops.conv_in_gemm(x3, ops.pack_conv_in(w3), b3, silu=True)
+    _close(out3, F.silu(F.conv2d(x3.float(), w3.float(), b3.float(), padding=1)).permute(0, 2, 3, 1), 2e-3, 2e-3, "conv_in_gemm silu")
     h = _rand((2, 64, 64, 320), 4)
     w2, b2 = _rand((4, 320, 3, 3), 5, (2880) ** -0.5), _rand((4,), 6, 0.1)
     out2 = ops.conv_out(h, pack_conv3x3(w2), b2)
     ref2 = F.conv2d(h.float().permute(0, 3, 1, 2), w2.float(), b2.float(), padding=1)
     _close(out2, ref2, 2e-3, 2e-3, "conv_out")
+    h5 = _rand((5, 16, 8, 320), 10)  # pixel count not a multiple of the CTA's 64 pixels x batch
+    out5 = ops.conv_out(h5, pack_conv3x3(w2), b2)
+    _close(out5, F.conv2d(h5.float().permute(0, 3, 1, 2), w2.float(), b2.float(), padding=1), 2e-3, 2e-3, "conv_out ragged")
 
 
 def test_timestep_embedding():

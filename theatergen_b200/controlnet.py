@@ -54,7 +54,7 @@ class TGControlNet(_BlockNet):
         dev = self.device
         g = _getter(sd, dev)
         w = {}
-        w["conv_in.w"], w["conv_in.b"] = g("conv_in.weight"), g("conv_in.bias")
+        w["conv_in.w"], w["conv_in.b"] = ops.pack_conv_in(g("conv_in.weight")), g("conv_in.bias")
         w["t1.w"], w["t1.b"] = g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias")
         w["t2.w"], w["t2.b"] = g("time_embedding.linear_2.weight"), g("time_embedding.linear_2.bias")
         self.resnets = {}
@@ -95,7 +95,7 @@ class TGControlNet(_BlockNet):
         pe = "controlnet_cond_embedding"
         c0 = _pad64(COND_CHANNELS[0])
         wp, bp = padded(pe + ".conv_in", c0, 3)
-        w["ce.in.w"], w["ce.in.b"] = wp.contiguous(), bp
+        w["ce.in.w"], w["ce.in.b"] = ops.pack_conv_in(wp.contiguous()), bp
         self.cond_layers = []  # (weight, bias, stride, cout_padded)
         for i in range(3):
             ci, co = _pad64(COND_CHANNELS[i]), _pad64(COND_CHANNELS[i + 1])
@@ -121,7 +121,7 @@ class TGControlNet(_BlockNet):
         w = self.w
         cond = cond.to(device=self.device, dtype=torch.float16).contiguous()
         n, _, H, W = cond.shape
-        h = ops.conv_in(cond, w["ce.in.w"], w["ce.in.b"], silu=True)
+        h = ops.conv_in_gemm(cond, w["ce.in.w"], w["ce.in.b"], silu=True)
         for wt, bs, stride, cout in self.cond_layers:
             if stride == 1:
                 h = ops.conv3x3(h, wt, bs, act=ops.TG_ACT_SILU)
@@ -141,7 +141,7 @@ class TGControlNet(_BlockNet):
         def tf(p, x, h_, w_):
             return self._transformer(p, x, ctxkv, B, h_, w_, T, 0, None, None, None, False, None)
 
-        x = ops.conv_in(sample, w["conv_in.w"], w["conv_in.b"])
+        x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
         per = H * W * 320
         n = cond_emb.shape[0]  # 1 (one image), K (rows [uncond K | cond K] share the K images) or B
         for b in range(B):  # + conditioning embedding

@@ -95,6 +95,10 @@ int tg_conv_in(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half*
   TG_CHECK(x && w && bias && y, "tg_conv_in: null pointer");
   return tg::conv_in_nchw_to_nhwc(H(x), H(w), H(bias), HM(y), B, Cin, Hh, W, Cout, silu, ST(stream));
 }
+int tg_im2col_small(const tg_half* x, tg_half* out, int B, int Cin, int Hh, int W, void* stream) {
+  TG_CHECK(x && out, "tg_im2col_small: null pointer");
+  return tg::im2col_small_nchw(H(x), HM(out), B, Cin, Hh, W, ST(stream));
+}
 int tg_conv_out(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int C,
                 void* stream) {
   TG_CHECK(x && w && bias && y, "tg_conv_out: null pointer");

@@ -139,45 +139,101 @@ int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, _
 // conv_out: NHWC [B,H,W,C] (already GroupNorm+SiLU-ed) -> NCHW [B,4,H,W], 3x3 pad 1
 // (ip_adapter/unet_2d_condition.py:1120).  One warp per output pixel; weights [4][3][3][C] via L1.
 // ---------------------------------------------------------------------------------------------------------
+// Weights [COUT][3][3][C] are staged ONCE per CTA in shared memory (23 KB at C = 320) and reused for the CTA's 64
+// pixels; a warp owns a pixel at a time, lanes split the channels (half2), warp-reduce at the end.  (The first version
+// re-read the weights through L1 for every pixel: 128 us at B = 10; this one is bound by the 9 input reads.)
+static constexpr int CONV_OUT_PIX = 64;
 template <int COUT>
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
                 __half* __restrict__ y, int B, int H, int W, int C) {
   grid_dep_launch();
   grid_dep_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int HW = H * W;
-  if (warp >= B * HW) return;
-  const int b = warp / HW, p = warp % HW, py = p / W, px = p % W;
-  float acc[COUT];
+  extern __shared__ __align__(16) uint8_t sm_co[];
+  __half2* sw = reinterpret_cast<__half2*>(sm_co);  // [COUT*9][C/2]
+  const int c2n = C / 2, HW = H * W;
+  for (int i = threadIdx.x; i < COUT * 9 * c2n; i += blockDim.x) sw[i] = reinterpret_cast<const __half2*>(w)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = B * HW;
+  for (int pi = warp; pi < CONV_OUT_PIX; pi += 8) {
+    const int gp = blockIdx.x * CONV_OUT_PIX + pi;
+    if (gp >= total) break;
+    const int b = gp / HW, p = gp % HW, py = p / W, px = p % W;
+    float acc[COUT];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-  const int c2n = C / 2;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xx) * C);
-    for (int c = lane; c < c2n; c += 32) {
-      const float2 xv = __half22float2(xp[c]);
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xx) * C);
+      for (int c = lane; c < c2n; c += 32) {
+        const float2 xv = __half22float2(xp[c]);
 #pragma unroll
-      for (int o = 0; o < COUT; ++o) {
-        const float2 wv = __half22float2(__ldg(reinterpret_cast<const __half2*>(w + ((size_t)o * 9 + tap) * C) + c));
-        acc[o] += xv.x * wv.x + xv.y * wv.y;
+        for (int o = 0; o < COUT; ++o) {
+          const float2 wv = __half22float2(sw[(o * 9 + tap) * c2n + c]);
+          acc[o] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, acc[o]));
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) {
-    const float s = warp_sum(acc[o]);
-    if (lane == 0) y[((size_t)b * COUT + o) * HW + p] = __float2half_rn(s + __half2float(bias[o]));
+    for (int o = 0; o < COUT; ++o) {
+      const float s_ = warp_sum(acc[o]);
+      if (lane == 0) y[((size_t)b * COUT + o) * HW + p] = __float2half_rn(s_ + __half2float(bias[o]));
+    }
   }
 }
 
 int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
                           cudaStream_t st) {
   TG_CHECK(C % 2 == 0, "conv_out: C odd");
-  const int warps = B * H * W;
-  TG_CUDA(launch_kernel(conv_out_kernel<4>, dim3((warps * 32 + 255) / 256), dim3(256), 0, st, 1, x, w, bias, y, B, H, W, C));
+  const size_t smem = (size_t)4 * 9 * C * 2;
+  static bool attr = false;
+  if (!attr) {
+    TG_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr = true;
+  }
+  TG_CHECK(smem <= 96 * 1024, "conv_out: C=%d too large", C);
+  const int total = B * H * W;
+  TG_CUDA(launch_kernel(conv_out_kernel<4>, dim3((total + CONV_OUT_PIX - 1) / CONV_OUT_PIX), dim3(256), smem, st, 1, x, w, bias, y, B, H, W, C));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// im2col of a small-channel NCHW image for a 3x3 / pad 1 / stride 1 convolution done as a tensor-core GEMM:
+// out[(b, y, x)][k] = x[b][ci][y + ky - 1][x + kx - 1] with k = ci * 9 + ky * 3 + kx (the flattening of a torch
+// [Cout][Cin][3][3] weight), columns k >= Cin * 9 zero (K padded to 64).  Used for conv_in (Cin = 4 latents,
+// ip_adapter/unet_2d_condition.py:999) and the first convolution of the ControlNet hint embedder (Cin = 3).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_small_kernel(const __half* __restrict__ x, uint4* __restrict__ out, int Cin, int H, int W, size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int HW = H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i & 7);  // 8 columns of the 64
+    const size_t pix = i >> 3;
+    const int p = (int)(pix % HW), py = p / W, px = p % W;
+    const size_t b = pix / HW;
+    uint4 v;
+    __half* hv = reinterpret_cast<__half*>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = chunk * 8 + j;
+      const int ci = k / 9, tap = k - ci * 9;
+      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
+      hv[j] = (ci < Cin && yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[((b * Cin + ci) * H + yy) * W + xx] : __float2half(0.f);
+    }
+    out[i] = v;
+  }
+}
+int im2col_small_nchw(const __half* x, __half* out, int B, int Cin, int H, int W, cudaStream_t st) {
+  TG_CHECK(Cin * 9 <= 64, "im2col_small: Cin=%d (Cin * 9 must fit 64 columns)", Cin);
+  const size_t total = (size_t)B * H * W * 8;
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 16) ? ((total + 255) / 256) : (size_t)(148 * 16));
+  TG_CUDA(launch_kernel(im2col_small_kernel, dim3(grid), dim3(256), 0, st, 1, x, reinterpret_cast<uint4*>(out), Cin, H, W, total));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

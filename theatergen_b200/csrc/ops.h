@@ -58,6 +58,8 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cuda
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaStream_t st);
 int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int H, int W,
                          int Cout, int silu, cudaStream_t st);
+// [B,Cin,H,W] NCHW -> [B*H*W, 64]: 3x3 patches flattened as k = ci*9 + tap, zero padded (Cin*9 <= 64)
+int im2col_small_nchw(const __half* x, __half* out, int B, int Cin, int H, int W, cudaStream_t st);
 int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
                           cudaStream_t st);
 int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st);

@@ -239,6 +239,28 @@ def conv_in(x_nchw, w, bias, out=None, silu=False):
     return out
 
 
+def pack_conv_in(w):
+    """torch [Cout,Cin,3,3] -> GEMM weight [Cout,64] (k = ci*9 + tap, zero padded) for conv_in_gemm."""
+    co, cin = w.shape[:2]
+    wp = torch.zeros((co, 64), dtype=torch.float16, device=w.device)
+    wp[:, :cin * 9] = w.reshape(co, cin * 9)
+    return wp
+
+
+def conv_in_gemm(x_nchw, w_packed, bias, silu=False, out=None):
+    """3x3 / pad 1 convolution of a small-channel NCHW image as im2col (K padded to 64) + tensor-core GEMM
+    -> NHWC [B,H,W,Cout]."""
+    _chk16(x_nchw, w_packed, bias, out)
+    B, Cin, H, W = x_nchw.shape
+    assert x_nchw.is_contiguous() and w_packed.shape[1] == 64 and Cin * 9 <= 64
+    cols = torch.empty((B * H * W, 64), dtype=torch.float16, device=x_nchw.device)
+    _lib.check(_lib.lib().tg_im2col_small(_p(x_nchw), _p(cols), B, Cin, H, W, _stream()), "tg_im2col_small")
+    Cout = w_packed.shape[0]
+    y = gemm(cols, w_packed, bias, act=TG_ACT_SILU if silu else TG_ACT_NONE,
+             out=None if out is None else out.view(B * H * W, Cout))
+    return y.view(B, H, W, Cout)
+
+
 def conv_out(x_nhwc, w, bias, out=None):
     """w packed [4,3,3,C]; returns NCHW [B,4,H,W]."""
     _chk16(x_nhwc, w, bias, out)

@@ -253,7 +253,7 @@ class TGUNet(_BlockNet):
         dev = self.device
         g = _getter(sd, dev)
         w = {}
-        w["conv_in.w"], w["conv_in.b"] = g("conv_in.weight"), g("conv_in.bias")
+        w["conv_in.w"], w["conv_in.b"] = ops.pack_conv_in(g("conv_in.weight")), g("conv_in.bias")
         w["t1.w"], w["t1.b"] = g("time_embedding.linear_1.weight"), g("time_embedding.linear_1.bias")
         w["t2.w"], w["t2.b"] = g("time_embedding.linear_2.weight"), g("time_embedding.linear_2.bias")
         self.resnets = {}
@@ -359,7 +359,7 @@ class TGUNet(_BlockNet):
                         ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
                 finally:
                     _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
-        x = ops.conv_in(sample, w["conv_in.w"], w["conv_in.b"])
+        x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
         x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
         if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
             skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
