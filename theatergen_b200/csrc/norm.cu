@@ -17,14 +17,15 @@ static constexpr int GN_GROUPS = 32;
 static constexpr int GN_MAX_SLABS = 64;
 static constexpr int GN_THREADS = 320;  // two-pass kernels: >= C/8 for C <= 2560
 static constexpr int GN_FUSED_THREADS = 512;
-static constexpr int GN_FUSED_CLUSTER = 8;
-static constexpr int GN_FUSED_MAX_STAGE = 168 * 1024;  // bytes of one CTA's slab kept on chip
+static constexpr int GN_FUSED_MAX_CLUSTER = 16;
+static constexpr int GN_FUSED_MAX_SMEM = 220 * 1024;   // slab + reduction scratch of one CTA (+ 4.7 KB static)
 static constexpr int GN_MAX_BATCH = 256;
 
 // tunables (tools/gn_bench.py sweeps them through tg_groupnorm_tune): slabs per image of the statistics kernel (a
 // function of the tensor shape only -- never of the batch -- so an image's statistics are summed in the same order
 // whatever batch it travels in), CTAs per SM of the apply kernel, and whether the single-kernel cluster path may be used
 static int g_gn_stats_slabs = 32, g_gn_apply_per_sm = 8, g_gn_fused = 1;  // measured best (tools/gn_bench.py, B=10)
+static bool g_gn_cluster16_ok = false;
 void groupnorm_tune(int stats_slabs, int apply_per_sm, int fused) {
   if (stats_slabs > 0) g_gn_stats_slabs = stats_slabs < GN_MAX_SLABS ? stats_slabs : GN_MAX_SLABS;
   if (apply_per_sm > 0) g_gn_apply_per_sm = apply_per_sm;
@@ -136,49 +137,81 @@ __device__ __forceinline__ uint4 gn_emit(const uint4& v, const float (&sa)[8], c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// single-kernel path: one cluster of GN_FUSED_CLUSTER CTAs per image.  Each CTA streams its slab of rows ONCE from
-// global memory into shared memory while accumulating the statistics, the eight CTAs exchange their 32 x (sum, sumsq)
-// through distributed shared memory, and the slab is normalised (+SiLU) straight out of shared memory: one HBM read, one
-// HBM write, one launch.  Possible whenever a slab (HW/8 rows x C) fits on chip (all 8x8 / 16x16 tensors and the
-// 640-channel 32x32 ones); used by default at the 8x8 level only, where it measured faster than the two launches of the
-// two-pass path.  The cluster size is a function of the tensor shape only, so an image's result does not depend on the
-// batch it travels in.
+// single-kernel path: one cluster of CS (2..16) CTAs per image.  One warp streams the CTA's slab of rows ONCE from global
+// memory into shared memory with bulk copies (cp.async.bulk: a row per copy, or the whole slab in one copy when it is
+// contiguous -- far more bytes in flight than register-staged loads can keep), all threads accumulate the statistics
+// out of shared memory, the CTAs exchange their 32 x (sum, sumsq) through distributed shared memory (one parallel
+// gather), and the slab is normalised (+SiLU) straight out of shared memory: one HBM read, one HBM write, one launch.
+// Possible whenever a slab (HW/CS rows x C) fits on chip next to the reduction scratch.  The cluster size is a
+// function of the tensor shape only, so an image's result does not depend on the batch it travels in.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gn_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __global__ void __launch_bounds__(GN_FUSED_THREADS, 1)
 gn_fused_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict__ x2, int C2, int HW,
                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
                 __half* __restrict__ out) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  __shared__ float s_grp[2 * GN_GROUPS];
+  __shared__ float s_gather[GN_FUSED_MAX_CLUSTER * 2 * GN_GROUPS];
+  __shared__ float s_stat[2 * GN_GROUPS];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int b = blockIdx.y, rank = blockIdx.x, CS = gridDim.x;  // gridDim.x == cluster size
+  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
+  const int rows_per = HW / CS;
+  const int r0 = rank * rows_per;
+  const int R = GN_FUSED_THREADS / c8n;
+  uint4* stage = reinterpret_cast<uint4*>(s_raw);  // [rows_per][C] fp16
+  float* s_lane = reinterpret_cast<float*>(s_raw + (size_t)rows_per * C * 2);
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   grid_dep_launch();
   grid_dep_wait();
-  extern __shared__ __align__(16) uint8_t s_raw[];
-  __shared__ float s_grp[2 * GN_GROUPS];
-  __shared__ float s_stat[2 * GN_GROUPS];
-  const int b = blockIdx.y, rank = blockIdx.x;  // gridDim.x == cluster size
-  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
-  const int rows_per = HW / GN_FUSED_CLUSTER;
-  const int r0 = rank * rows_per, r1 = r0 + rows_per;
-  const int R = GN_FUSED_THREADS / c8n;
-  uint4* stage = reinterpret_cast<uint4*>(s_raw);
-  float* s_lane = reinterpret_cast<float*>(s_raw + (size_t)rows_per * C * 2);
+  if (threadIdx.x < 32) {  // one warp issues the bulk copies
+    const uint32_t slab_bytes = (uint32_t)rows_per * C * 2;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, slab_bytes);
+    __syncwarp();
+    if (C2 == 0) {  // contiguous slab: a few large copies
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(x1 + ((size_t)b * HW + r0) * C);
+      const uint32_t piece = ((slab_bytes / 32) + 15) & ~15u;
+      const uint32_t off = threadIdx.x * piece;
+      if (off < slab_bytes) gn_bulk_load(s_raw + off, src + off, min(piece, slab_bytes - off), &s_bar);
+    } else {        // channel-concat of two tensors: one copy per row and source
+      for (int r = threadIdx.x; r < rows_per; r += 32) {
+        uint8_t* dst = s_raw + (size_t)r * C * 2;
+        gn_bulk_load(dst, x1 + ((size_t)b * HW + r0 + r) * C1, C1 * 2, &s_bar);
+        gn_bulk_load(dst + C1 * 2, x2 + ((size_t)b * HW + r0 + r) * C2, C2 * 2, &s_bar);
+      }
+    }
+  }
+  mbar_wait(&s_bar, 0);
+
   const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
   const bool active = rl < R;
   const int c = chunk * 8;
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  if (active) {
-    const __half* src;
-    int ld;
-    if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
-    src += (size_t)b * HW * ld;
-    gn_accumulate<true>(src, ld, r0, r1, R, rl, s, q, stage, c8n, chunk);
-  }
+  if (active)
+    for (int r = rl; r < rows_per; r += R) gn_acc8(stage[(size_t)r * c8n + chunk], s, q);
   gn_reduce_groups(s, q, active, C, cpg, R, rl, c, s_lane, s_grp);
   gn_cluster_arrive();
   gn_cluster_wait();  // every CTA's s_grp is complete and visible
+  for (int i = threadIdx.x; i < CS * 2 * GN_GROUPS; i += GN_FUSED_THREADS)  // one parallel gather of all ranks' partials
+    s_gather[i] = ld_dsmem_f32(&s_grp[i & (2 * GN_GROUPS - 1)], (uint32_t)(i / (2 * GN_GROUPS)));
+  gn_cluster_arrive();  // my remote reads are issued and complete (peers may exit once everybody has arrived)
+  __syncthreads();
   if (threadIdx.x < 2 * GN_GROUPS) {
     float a = 0.f;
-    for (uint32_t k = 0; k < GN_FUSED_CLUSTER; ++k) a += ld_dsmem_f32(&s_grp[threadIdx.x], k);  // fixed order
+    for (int k = 0; k < CS; ++k) a += s_gather[k * 2 * GN_GROUPS + threadIdx.x];  // fixed order
     const float other = __shfl_xor_sync(0xffffffffu, a, 1);  // lanes (2g, 2g+1) = (sum, sumsq)
     const float n = (float)HW * cpg;
     const float sum = (threadIdx.x & 1) ? other : a, sq = (threadIdx.x & 1) ? a : other;
@@ -186,14 +219,13 @@ gn_fused_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     const float var = fmaxf(sq / n - mean * mean, 0.f);
     s_stat[threadIdx.x] = (threadIdx.x & 1) ? rsqrtf(var + eps) : mean;
   }
-  gn_cluster_arrive();  // my remote reads are done (peers may exit once everybody has arrived)
   __syncthreads();
   if (active) {
     float sa[8], sb[8];
     gn_scale_shift(s_stat, gamma, beta, c, cpg, sa, sb);
-    __half* dst = out + (size_t)b * HW * C + c;
-    for (int r = r0 + rl; r < r1; r += R)
-      *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(stage[(size_t)(r - r0) * c8n + chunk], sa, sb, silu);
+    __half* dst = out + ((size_t)b * HW + r0) * C + c;
+    for (int r = rl; r < rows_per; r += R)
+      *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(stage[(size_t)r * c8n + chunk], sa, sb, silu);
   }
   gn_cluster_wait();
 }
@@ -307,20 +339,42 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   static bool attr = false;
   if (!attr) {
     TG_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    TG_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    TG_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_FUSED_MAX_SMEM));
+    // clusters of 16 are beyond the portable size: opt in and ask the occupancy calculator whether one fits at all
+    g_gn_cluster16_ok = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (g_gn_cluster16_ok) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(16, 1);
+      cfg.blockDim = dim3(GN_FUSED_THREADS);
+      cfg.dynamicSmemBytes = GN_FUSED_MAX_SMEM - 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      g_gn_cluster16_ok = cudaOccupancyMaxActiveClusters(&nclusters, gn_fused_kernel, &cfg) == cudaSuccess && nclusters > 0;
+    }
+    (void)cudaGetLastError();
     attr = true;
   }
   // ---- single-kernel cluster path ----
-  // g_gn_fused: 1 = where it measured faster than the two-pass kernels (the 8x8 level: a cluster launch costs more than
-  // a plain one, which only pays off when it replaces two launches over a tiny tensor), 2 = wherever a slab fits on chip
-  if (g_gn_fused && HW % GN_FUSED_CLUSTER == 0 && (HW <= 64 || g_gn_fused == 2)) {
-    const int rows_per = HW / GN_FUSED_CLUSTER;
-    const size_t stage = (size_t)rows_per * C * 2;
+  // g_gn_fused: 0 = never (two-pass kernels); otherwise wherever a slab fits on chip with a cluster of 8 or 16 CTAs per
+  // image -- measured faster than the two-pass kernels at every such shape (tools/gn_bench.py, B = 10: 25.5 vs 27 us at
+  // 64x64x320, 11.7 vs 15 at 32x32x640, 9.2 vs 14 at 16x16x1280, 7 vs 12 at 8x8) once SiLU costs one MUFU operation.
+  if (g_gn_fused) {
     const int Rf = GN_FUSED_THREADS / (C / 8);
-    const size_t smem = stage + (size_t)2 * Rf * C * sizeof(float);
-    if (stage <= GN_FUSED_MAX_STAGE && smem <= 222 * 1024) {
-      TG_CUDA(launch_kernel(gn_fused_kernel, dim3(GN_FUSED_CLUSTER, B), dim3(GN_FUSED_THREADS), smem, st,
-                            GN_FUSED_CLUSTER, x1, C1, x2, C2, HW, gamma, beta, eps, silu, out));
+    const size_t scratch = (size_t)2 * Rf * C * sizeof(float);
+    int cs = 0;
+    for (int cand = 8; cand <= GN_FUSED_MAX_CLUSTER; cand *= 2) {  // >= 8 CTAs per image for parallelism
+      if (HW % cand) break;
+      if ((size_t)(HW / cand) * C * 2 + scratch <= GN_FUSED_MAX_SMEM - 1024) { cs = cand; break; }
+    }
+    if (cs == 16 && !g_gn_cluster16_ok) cs = 0;
+    if (cs) {
+      const size_t smem = (size_t)(HW / cs) * C * 2 + scratch;
+      TG_CUDA(launch_kernel(gn_fused_kernel, dim3(cs, B), dim3(GN_FUSED_THREADS), smem, st, cs, x1, C1, x2, C2, HW, gamma, beta,
+                            eps, silu, out));
       TG_COUNT_LAUNCH();
       TG_LAUNCH_CHECK();
       return 0;
