@@ -16,8 +16,13 @@
 //   warps 2..5  one query row per thread (row == TMEM lane): Q row -> TMEM once; per tile S_j -> registers, softmax
 //               numerators, P_j -> fp16 pairs -> tcgen05.st INTO THE COLUMNS OF S_j (P overlays S: the tensor pipe executes
 //               in issue order, so S_{j+2} cannot overwrite P_j before P_j V_j has read it -- no extra barrier).
-//               (Measured: splitting a row's 64 columns over two warps -- 8 softmax warps, row max exchanged through
-//               shared memory -- is 8 % slower: the tile is paced by TMEM->register bandwidth, not by warp latency.)
+//               Measured alternatives that did NOT help (B = 10, N = 4096, d = 40: 504 us as shipped): 8 softmax warps
+//               splitting a row's 64 columns with the row max exchanged through shared memory (530 us); S loaded in four
+//               16-column chunks with speculative exponentials against the stale reference so a chunk's TMEM load
+//               overlaps the previous chunk's MUFU work (531 us); 1/6, 1/4, 1/2 of the exponentials on the FMA pipes by a
+//               degree-4 polynomial (531 / 563 / 629 us).  Every added instruction costs time and removing MUFU work does
+//               not pay: the softmax warps are bound by their own instruction stream (about 275 instructions per row
+//               and tile at two warps per scheduler), not by the MUFU or TMEM ports.
 // What bounds this kernel is TMEM->register bandwidth and the MUFU pipe, so the design minimises both:
 //   * O is accumulated IN TMEM across all KV tiles (accumulate flag) and is read exactly once, at the end.
 //     The running max is only a reference exponent: it is raised -- and O rescaled in TMEM (tcgen05.ld / st)
