@@ -22,7 +22,9 @@
 //               overlaps the previous chunk's MUFU work (531 us); 1/6, 1/4, 1/2 of the exponentials on the FMA pipes by a
 //               degree-4 polynomial (531 / 563 / 629 us).  Every added instruction costs time and removing MUFU work does
 //               not pay: the softmax warps are bound by their own instruction stream (about 275 instructions per row
-//               and tile at two warps per scheduler), not by the MUFU or TMEM ports.
+//               and tile at two warps per scheduler), not by the MUFU or TMEM ports.  A packed-half2 softmax (HMNMX2 /
+//               HFMA2 / h2exp2) is no shorter in SASS (h2exp2 unpacks to two fp32 MUFU.EX2 and repacks: 540 us) and
+//               fails the 2e-3 parity tolerance.
 // What bounds this kernel is TMEM->register bandwidth and the MUFU pipe, so the design minimises both:
 //   * O is accumulated IN TMEM across all KV tiles (accumulate flag) and is read exactly once, at the end.
 //     The running max is only a reference exponent: it is raised -- and O rescaled in TMEM (tcgen05.ld / st)
