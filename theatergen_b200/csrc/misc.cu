@@ -163,16 +163,42 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, cons
     float acc[COUT];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int yy = py + tap / 3 - 1, xx = px + tap % 3 - 1;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xx) * C);
-      for (int c = lane; c < c2n; c += 32) {
-        const float2 xv = __half22float2(xp[c]);
+    // a filter row (3 taps) at a time: all of its loads are issued before any is used (out-of-image taps read a valid
+    // address and are multiplied by zero), so a lane keeps 3 x ceil(C/64) independent loads in flight
+    constexpr int MAXI = 5;  // C <= 320
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+      __half2 xv[3][MAXI];
+      float ok[3];
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-          const float2 wv = __half22float2(sw[(o * 9 + tap) * c2n + c]);
-          acc[o] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, acc[o]));
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        ok[kx] = (xx >= 0 && xx < W) ? 1.f : 0.f;
+        const int xc = min(max(xx, 0), W - 1);
+        const __half2* xp = reinterpret_cast<const __half2*>(x + (((size_t)b * H + yy) * W + xc) * C);
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i) {
+          const int c = lane + 32 * i;
+          xv[kx][i] = c < c2n ? xp[c] : __half2{};
+        }
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tap = ky * 3 + kx;
+#pragma unroll
+        for (int i = 0; i < MAXI; ++i) {
+          const int c = lane + 32 * i;
+          if (c < c2n) {
+            float2 xf = __half22float2(xv[kx][i]);
+            xf.x *= ok[kx];
+            xf.y *= ok[kx];
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+              const float2 wv = __half22float2(sw[(o * 9 + tap) * c2n + c]);
+              acc[o] = fmaf(xf.x, wv.x, fmaf(xf.y, wv.y, acc[o]));
+            }
+          }
         }
       }
     }
@@ -186,7 +212,7 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, cons
 
 int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
                           cudaStream_t st) {
-  TG_CHECK(C % 2 == 0, "conv_out: C odd");
+  TG_CHECK(C % 2 == 0 && C <= 320, "conv_out: C=%d (even, <= 320)", C);
   const size_t smem = (size_t)4 * 9 * C * 2;
   static bool attr = false;
   if (!attr) {

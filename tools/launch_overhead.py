@@ -46,6 +46,12 @@ def main():
         x, g_, b_ = r(B, HW, C), r(C), r(C)
         o = torch.empty_like(x)
         rows.append((f"groupnorm B={B} HW={HW} C={C}", graph_us(lambda: ops.groupnorm(x, g_, b_, 1e-5, silu=True, out=o))))
+    from theatergen_b200.weights import pack_conv3x3
+    h, wo, bo = r(10, 64, 64, 320), pack_conv3x3(r(4, 320, 3, 3)), r(4)
+    oo = torch.empty(10, 4, 64, 64, device="cuda", dtype=torch.float16)
+    rows.append(("conv_out B=10 64x64x320 -> 4", graph_us(lambda: ops.conv_out(h, wo, bo, out=oo), n=16)))
+    xi, wi, bi = r(10, 4, 64, 64), ops.pack_conv_in(r(320, 4, 3, 3)), r(320)
+    rows.append(("conv_in (im2col + gemm) B=10 4 -> 320", graph_us(lambda: ops.conv_in_gemm(xi, wi, bi), n=16)))
     y, x2 = r(4096), r(4096)
     rows.append(("add_inplace 4096", graph_us(lambda: ops.add_inplace(y, x2))))
     for name, us in rows:
