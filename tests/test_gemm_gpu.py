@@ -20,7 +20,8 @@ def _close(got, ref, atol, rtol):
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 64), (256, 128, 320), (8192, 320, 320),
                                    (2048, 640, 2560), (512, 1280, 1280), (162, 1280, 768), (2, 1280, 320),
                                    (300, 192, 128), (512, 1280, 11520), (128, 1280, 2560), (2048, 960, 320),
-                                   (1024, 2560, 640), (256, 49920, 768)])
+                                   (1024, 2560, 640), (256, 49920, 768), (2560, 1280, 1280), (2560, 1280, 11520),
+                                   (40960, 320, 1280), (10240, 640, 2560), (6400, 1280, 5120), (2432, 1280, 2560)])
 def test_gemm_plain(M, N, K):
     from theatergen_b200 import ops
     a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
@@ -54,6 +55,19 @@ def test_gemm_splitk_with_epilogue_is_deterministic():
         assert torch.equal(out, ops.gemm(a, w, bias, rowbias=rowbias, rows_per_image=64, residual=res))
 
 
+def test_gemm_residual_is_deterministic_on_partial_waves():
+    """Shapes whose tile count does not fill whole waves (50 / 320 pair tiles on 74 workers): bit-reproducible results."""
+    from theatergen_b200 import ops
+    for M, N, K in ((2560, 1280, 5760), (40960, 320, 640)):
+        a, w = _rand((M, K), 1), _rand((N, K), 2, K ** -0.5)
+        bias, res = _rand((N,), 3), _rand((M, N), 4)
+        out = ops.gemm(a, w, bias, residual=res)
+        ref = a.float() @ w.float().t() + bias.float() + res.float()
+        _close(out, ref, 3e-3, 2e-3)
+        for _ in range(3):
+            assert torch.equal(out, ops.gemm(a, w, bias, residual=res))
+
+
 def test_gemm_two_sources_and_strided_out():
     from theatergen_b200 import ops
     M, N, K1, K2 = 256, 128, 128, 192
@@ -80,7 +94,7 @@ def test_gemm_geglu():
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 64, 64), (2, 64, 64, 320, 320), (2, 32, 32, 640, 640),
                                             (2, 16, 16, 1280, 1280), (2, 8, 8, 1280, 1280), (4, 8, 8, 2560, 1280),
-                                            (1, 32, 32, 960, 640)])
+                                            (1, 32, 32, 960, 640), (10, 16, 16, 1280, 1280), (10, 64, 64, 320, 320)])
 def test_conv3x3(B, H, W, Cin, Cout):
     from theatergen_b200 import ops
     x = _rand((B, H, W, Cin), 1)
