@@ -61,7 +61,7 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
 
 /* out = [SiLU](GroupNorm32([x1|x2])) for channels-last x1 [B,HW,C1], x2 [B,HW,C2] (x2 NULL when C2 == 0).
  * The up-path torch.cat([hidden, skip], 1) (ip_adapter/unet_2d_blocks.py:2210-2212, 2318-2320) is folded in.
- * workspace: >= 16640 + B*4096 floats, ZERO-INITIALISED once (holds self-resetting arrival counters); B <= 256.
+ * workspace: >= 16640 + B*16384 floats, ZERO-INITIALISED once (holds self-resetting arrival counters); B <= 256.
  * Replaces nn.GroupNorm(+SiLU) of diffusers ResnetBlock2D (eps 1e-5),
  * Transformer2DModel.norm (ip_adapter/transformer_2d.py:288, eps 1e-6), conv_norm_out
  * (ip_adapter/unet_2d_condition.py:1117-1119). */
@@ -126,8 +126,16 @@ int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_
  * [Cout][Cin][3][3] weight flattened), zero beyond Cin*9.  conv_in (unet_2d_condition.py:999) and the ControlNet hint
  * embedder's first convolution then run as tg_gemm with K = 64. */
 int tg_im2col_small(const tg_half* x_nchw, tg_half* out, int B, int Cin, int H, int W, void* stream);
+/* conv_out: NHWC [B,H,W,C] -> NCHW [B,Cout,H,W], 3x3 pad 1, w = [Cout,3,3,C]; Cout = 4 (UNet eps,
+ * unet_2d_condition.py:1120) or 3 (VAE decoder RGB, models/pipelines.py:468, 162-173) */
 int tg_conv_out(const tg_half* x_nhwc, const tg_half* w, const tg_half* bias, tg_half* y_nchw, int B, int H,
-                int W, int C, void* stream);
+                int W, int C, int Cout, void* stream);
+/* 1x1 convolution between tiny channel counts on NCHW (diffusers AutoencoderKL.post_quant_conv on the latents) */
+int tg_pointwise_nchw(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Cin, int Cout,
+                      int HW, void* stream);
+/* out[r,:] = softmax(scale * x[r,:]) in fp32, one row per CTA, N <= 8192 (the single-head 512-channel attention of the
+ * VAE mid block runs as tg_gemm -> tg_softmax_rows -> tg_gemm; diffusers Attention with upcast_softmax) */
+int tg_softmax_rows(const tg_half* x, int ldx, tg_half* out, int ldo, int M, int N, float scale, void* stream);
 int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream);
 int tg_add_inplace(tg_half* y, const tg_half* x, long long n, void* stream);
 int tg_nchw_to_nhwc(const tg_half* x, tg_half* y, int B, int C, int HW, void* stream);

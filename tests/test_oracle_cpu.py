@@ -168,3 +168,18 @@ def test_controlnet_oracle_structure_and_determinism():
         a = OU.unet_forward(sdu, x, 981, ctx81, ip_scale=0.1)
         b = OU.unet_forward(sdu, x, 981, ctx81, ip_scale=0.1, down_residuals=down, mid_residual=mid)
     assert torch.equal(a, b)
+
+
+def test_vae_decoder_oracle_structure():
+    """oracle/vae.py: diffusers AutoencoderKL decoder key set with the published parameter count of the SD VAE decoder
+    (49,490,179 + 20 for post_quant_conv), 8x upsampling."""
+    from oracle import vae as OV
+    sd = OV.synth_state_dict(777)
+    assert sum(v.numel() for v in sd.values()) == 49_490_199
+    assert "decoder.mid_block.attentions.0.to_q.weight" in sd and "decoder.up_blocks.3.resnets.2.conv2.weight" in sd
+    assert sd["decoder.up_blocks.2.resnets.0.conv_shortcut.weight"].shape == (256, 512, 1, 1)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(1, 4, 16, 16, generator=g)  # small latent: the decoder is fully convolutional
+    with torch.no_grad():
+        img = OV.decode(sd, z)
+    assert img.shape == (1, 3, 128, 128) and torch.isfinite(img).all()

@@ -32,7 +32,9 @@ _SIGS = {
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, vp]),
     "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_im2col_small": (ci, [vp, vp, ci, ci, ci, ci, vp]),
-    "tg_conv_out": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_conv_out": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),
+    "tg_pointwise_nchw": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_softmax_rows": (ci, [vp, ci, vp, ci, ci, ci, cf, vp]),
     "tg_timestep_embedding": (ci, [vp, vp, ci, ci, vp]),
     "tg_add_inplace": (ci, [vp, vp, C.c_longlong, vp]),
     "tg_nchw_to_nhwc": (ci, [vp, vp, ci, ci, ci, vp]),

@@ -100,9 +100,18 @@ int tg_im2col_small(const tg_half* x, tg_half* out, int B, int Cin, int Hh, int 
   return tg::im2col_small_nchw(H(x), HM(out), B, Cin, Hh, W, ST(stream));
 }
 int tg_conv_out(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Hh, int W, int C,
-                void* stream) {
+                int Cout, void* stream) {
   TG_CHECK(x && w && bias && y, "tg_conv_out: null pointer");
-  return tg::conv_out_nhwc_to_nchw(H(x), H(w), H(bias), HM(y), B, Hh, W, C, ST(stream));
+  return tg::conv_out_nhwc_to_nchw(H(x), H(w), H(bias), HM(y), B, Hh, W, C, Cout, ST(stream));
+}
+int tg_pointwise_nchw(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Cin, int Cout, int HW,
+                      void* stream) {
+  TG_CHECK(x && w && bias && y, "tg_pointwise_nchw: null pointer");
+  return tg::pointwise_nchw(H(x), H(w), H(bias), HM(y), B, Cin, Cout, HW, ST(stream));
+}
+int tg_softmax_rows(const tg_half* x, int ldx, tg_half* out, int ldo, int M, int N, float scale, void* stream) {
+  TG_CHECK(x && out && M > 0, "tg_softmax_rows: bad arguments");
+  return tg::softmax_rows(H(x), ldx, HM(out), ldo, M, N, scale, ST(stream));
 }
 int tg_timestep_embedding(const float* t_dev, tg_half* out, int B, int dim, void* stream) {
   TG_CHECK(t_dev && out && dim % 2 == 0, "tg_timestep_embedding: bad arguments");

@@ -210,18 +210,113 @@ conv_out_kernel(const __half* __restrict__ x, const __half* __restrict__ w, cons
   }
 }
 
-int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
-                          cudaStream_t st) {
-  TG_CHECK(C % 2 == 0 && C <= 320, "conv_out: C=%d (even, <= 320)", C);
-  const size_t smem = (size_t)4 * 9 * C * 2;
+template <int COUT>
+static int conv_out_launch(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
+                           cudaStream_t st) {
+  const size_t smem = (size_t)COUT * 9 * C * 2;
   static bool attr = false;
   if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    TG_CUDA(cudaFuncSetAttribute(conv_out_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr = true;
   }
   TG_CHECK(smem <= 96 * 1024, "conv_out: C=%d too large", C);
   const int total = B * H * W;
-  TG_CUDA(launch_kernel(conv_out_kernel<4>, dim3((total + CONV_OUT_PIX - 1) / CONV_OUT_PIX), dim3(256), smem, st, 1, x, w, bias, y, B, H, W, C));
+  TG_CUDA(launch_kernel(conv_out_kernel<COUT>, dim3((total + CONV_OUT_PIX - 1) / CONV_OUT_PIX), dim3(256), smem, st, 1, x, w, bias, y, B, H, W, C));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// Cout = 4: the UNet's conv_out (eps); Cout = 3: the VAE decoder's conv_out (RGB)
+int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
+                          int Cout, cudaStream_t st) {
+  TG_CHECK(C % 2 == 0 && C <= 320, "conv_out: C=%d (even, <= 320)", C);
+  if (Cout == 4) return conv_out_launch<4>(x, w, bias, y, B, H, W, C, st);
+  if (Cout == 3) return conv_out_launch<3>(x, w, bias, y, B, H, W, C, st);
+  TG_CHECK(false, "conv_out: Cout=%d unsupported (3 or 4)", Cout);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1x1 convolution between tiny channel counts on an NCHW tensor (the VAE's post_quant_conv, 4 -> 4, on the latents):
+// y[b, o, p] = bias[o] + sum_c w[o, c] x[b, c, p]
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pointwise_nchw_kernel(const __half* __restrict__ x, const __half* __restrict__ w, const __half* __restrict__ bias,
+                      __half* __restrict__ y, int Cin, int Cout, int HW, int total) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i % HW, o = (i / HW) % Cout, b = i / (HW * Cout);
+    float acc = __half2float(bias[o]);
+    for (int c = 0; c < Cin; ++c) acc = fmaf(__half2float(w[o * Cin + c]), __half2float(x[((size_t)b * Cin + c) * HW + p]), acc);
+    y[i] = __float2half_rn(acc);
+  }
+}
+int pointwise_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int Cout, int HW,
+                   cudaStream_t st) {
+  TG_CHECK(Cin >= 1 && Cin <= 16 && Cout >= 1 && Cout <= 16, "pointwise: Cin=%d Cout=%d (1..16)", Cin, Cout);
+  const int total = B * Cout * HW;
+  TG_CUDA(launch_kernel(pointwise_nchw_kernel, dim3((total + 255) / 256), dim3(256), 0, st, 1, x, w, bias, y, Cin, Cout, HW, total));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row softmax: out[r, :] = softmax(scale * x[r, :]) in fp32 (the VAE mid-block attention: one head of 512 channels over
+// 4096 tokens is computed as GEMM -> this -> GEMM; diffusers upcasts that softmax).  One CTA per row, N <= 8192.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ out, int ldo, int N, float scale_log2) {
+  grid_dep_launch();
+  grid_dep_wait();
+  __shared__ float s_red[8];
+  const __half2* px = reinterpret_cast<const __half2*>(x + (size_t)blockIdx.x * ldx);
+  __half2* po = reinterpret_cast<__half2*>(out + (size_t)blockIdx.x * ldo);
+  const int n2 = N / 2, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 v[16];  // up to 8192 columns
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < n2) {
+      v[i] = __half22float2(px[c]);
+      mx = fmaxf(mx, fmaxf(v[i].x, v[i].y));
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < n2) {
+      v[i].x = exp2f((v[i].x - mx) * scale_log2);
+      v[i].y = exp2f((v[i].y - mx) * scale_log2);
+      sum += v[i].x + v[i].y;
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += s_red[i];
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < n2) po[c] = __floats2half2_rn(v[i].x * inv, v[i].y * inv);
+  }
+}
+int softmax_rows(const __half* x, int ldx, __half* out, int ldo, int M, int N, float scale, cudaStream_t st) {
+  TG_CHECK(N % 2 == 0 && N <= 8192 && ldx % 2 == 0 && ldo % 2 == 0 && scale > 0.f, "softmax_rows: N=%d (even, <= 8192), scale > 0", N);
+  TG_CUDA(launch_kernel(softmax_rows_kernel, dim3(M), dim3(256), 0, st, 1, x, ldx, out, ldo, N, scale * 1.4426950408889634f));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

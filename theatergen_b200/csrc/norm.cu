@@ -14,7 +14,7 @@
 namespace tg {
 
 static constexpr int GN_GROUPS = 32;
-static constexpr int GN_MAX_SLABS = 64;
+static constexpr int GN_MAX_SLABS = 256;
 static constexpr int GN_THREADS = 320;  // two-pass kernels: >= C/8 for C <= 2560
 static constexpr int GN_FUSED_THREADS = 512;
 static constexpr int GN_FUSED_MAX_CLUSTER = 16;
@@ -381,9 +381,12 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
     }
   }
   // ---- two-pass path ----
-  TG_CHECK(workspace != nullptr, "groupnorm: zero-initialised workspace (16640 + B*4096 floats) required");
+  TG_CHECK(workspace != nullptr, "groupnorm: zero-initialised workspace (16640 + B*16384 floats) required");
   const int R = GN_THREADS / (C / 8);
-  const int slabs = max(1, min(g_gn_stats_slabs, HW / max(1, 2 * R)));
+  // slabs per image: a function of the tensor shape only; the VAE decoder's 256x256 / 512x512 tensors (HW = 64 K / 256 K
+  // at batch 1) get up to 256
+  const int want = max(g_gn_stats_slabs, HW / 512);
+  const int slabs = max(1, min(min(want, GN_MAX_SLABS), HW / max(1, 2 * R)));
   const size_t smem = (size_t)2 * R * C * sizeof(float);
   TG_CHECK(smem <= 64 * 1024, "groupnorm: smem %zu too large", smem);
   // workspace layout (fixed offsets, independent of B): [256 arrival counters][256 x 32 x (mean, rstd)][partials]

@@ -61,7 +61,10 @@ int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, _
 // [B,Cin,H,W] NCHW -> [B*H*W, 64]: 3x3 patches flattened as k = ci*9 + tap, zero padded (Cin*9 <= 64)
 int im2col_small_nchw(const __half* x, __half* out, int B, int Cin, int H, int W, cudaStream_t st);
 int conv_out_nhwc_to_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
-                          cudaStream_t st);
+                          int Cout, cudaStream_t st);
+int pointwise_nchw(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int Cout, int HW,
+                   cudaStream_t st);
+int softmax_rows(const __half* x, int ldx, __half* out, int ldo, int M, int N, float scale, cudaStream_t st);
 int timestep_embedding(const float* t_dev, __half* out, int B, int dim, cudaStream_t st);
 int add_inplace(__half* y, const __half* x, size_t n, cudaStream_t st);
 int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t st);

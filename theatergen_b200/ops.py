@@ -76,6 +76,7 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
          out_scale=1.0, out=None):
     """out[M,N] = act([a|a2] @ w.T + bias + rowbias[row // rows_per_image]) + residual ; w is [N,K]."""
     _chk16(a, w, bias, a2, rowbias, residual, out)
+    assert w.is_contiguous(), "gemm: the weight operand must be a dense [N,K] matrix"
     M, K1 = a.shape
     N, K = w.shape
     if a2 is not None:
@@ -120,9 +121,9 @@ _GN_WS = {}
 def _gn_workspace(device, B):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _GN_WS.get(key)
-    if ws is None or ws.numel() < 16640 + B * 4096:
-        # [256 arrival counters (start at zero, self-resetting)][256x32x2 mean/rstd][partials B x 64 x 32 x 2]
-        ws = torch.zeros(16640 + max(B, 32) * 4096, dtype=torch.float32, device=device)
+    if ws is None or ws.numel() < 16640 + B * 16384:
+        # [256 arrival counters (start at zero, self-resetting)][256x32x2 mean/rstd][partials B x 256 x 32 x 2]
+        ws = torch.zeros(16640 + max(B, 16) * 16384, dtype=torch.float32, device=device)
         _GN_WS[key] = ws
     return ws
 
@@ -262,12 +263,36 @@ def conv_in_gemm(x_nchw, w_packed, bias, silu=False, out=None):
 
 
 def conv_out(x_nhwc, w, bias, out=None):
-    """w packed [4,3,3,C]; returns NCHW [B,4,H,W]."""
+    """w packed [Cout,3,3,C] with Cout 3 or 4; returns NCHW [B,Cout,H,W]."""
     _chk16(x_nhwc, w, bias, out)
     B, H, W, Cc = x_nhwc.shape
+    cout = w.shape[0]
     if out is None:
-        out = torch.empty((B, 4, H, W), dtype=torch.float16, device=x_nhwc.device)
-    _lib.check(_lib.lib().tg_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(out), B, H, W, Cc, _stream()), "tg_conv_out")
+        out = torch.empty((B, cout, H, W), dtype=torch.float16, device=x_nhwc.device)
+    _lib.check(_lib.lib().tg_conv_out(_p(x_nhwc), _p(w), _p(bias), _p(out), B, H, W, Cc, cout, _stream()), "tg_conv_out")
+    return out
+
+
+def pointwise_nchw(x, w, bias, out=None):
+    """1x1 convolution between tiny channel counts: x NCHW [B,Cin,H,W], w [Cout,Cin] -> NCHW [B,Cout,H,W]."""
+    _chk16(x, w, bias, out)
+    B, Cin, H, W = x.shape
+    cout = w.shape[0]
+    assert x.is_contiguous() and w.is_contiguous() and w.shape[1] == Cin
+    if out is None:
+        out = torch.empty((B, cout, H, W), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_pointwise_nchw(_p(x), _p(w), _p(bias), _p(out), B, Cin, cout, H * W, _stream()), "tg_pointwise_nchw")
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    """out[r,:] = softmax(scale * x[r,:]) (fp32 math), x [M,N] fp16 with N <= 8192."""
+    _chk16(x, out)
+    M, N = x.shape
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_softmax_rows(_p(x), x.stride(0), _p(out), out.stride(0), M, N, float(scale), _stream()),
+               "tg_softmax_rows")
     return out
 
 
