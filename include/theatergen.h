@@ -118,7 +118,12 @@ int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg
 /* layout / small ops of the UNet forward (ip_adapter/unet_2d_condition.py:897-902, 999, 1044-1053, 1117-1120;
  * diffusers Upsample2D / Downsample2D) */
 int tg_upsample2x(const tg_half* x, int B, int H, int W, int C, tg_half* y, void* stream);
-int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, void* stream);
+/* pad_lo = 1: symmetric padding 1 (UNet / ControlNet Downsample2D); pad_lo = 0: the VAE encoder's F.pad(x,(0,1,0,1)) */
+int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, int pad_lo, void* stream);
+/* diffusers DiagonalGaussianDistribution.sample on NCHW moments [B,2L,HW]: z = (mean + exp(0.5 clamp(logvar,-30,20)) *
+ * noise) * out_scale; noise NULL = the mode (models/pipelines.py:624-626) */
+int tg_gaussian_sample(const tg_half* moments, const tg_half* noise, tg_half* z, int B, int L, int HW, float out_scale,
+                       void* stream);
 /* conv_in: NCHW [B,Cin,H,W] (Cin = 4 latents, or 3 for the ControlNet hint image) -> NHWC [B,H,W,Cout], optional SiLU */
 int tg_conv_in(const tg_half* x_nchw, const tg_half* w, const tg_half* bias, tg_half* y_nhwc, int B, int Cin, int H,
                int W, int Cout, int silu, void* stream);

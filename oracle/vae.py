@@ -1,4 +1,4 @@
-"""Functional restatement of the SD-1.5 VAE DECODER (TEST INFRASTRUCTURE, see oracle/__init__.py).
+"""Functional restatement of the SD-1.5 VAE, decoder and encoder (TEST INFRASTRUCTURE, see oracle/__init__.py).
 
 The reference builds the stock diffusers `AutoencoderKL` (`stabilityai/sd-vae-ft-mse`, generate.py:59,77) and decodes
 K + 1 latents per turn: `vae.decode(latents / scaling_factor, return_dict=False)[0]` at the end of stage 1
@@ -12,6 +12,11 @@ K + 1 latents per turn: `vae.decode(latents / scaling_factor, return_dict=False)
   up i : 3 x ResnetBlock2D (512,512 | 512,512 | 512->256,256 | 256->128,128), nearest x2 + conv3x3 after blocks 0..2
   out  = conv_out(silu(GroupNorm(32, eps 1e-6)(h)))          (3x3, 128 -> 3)
 ResnetBlock2D here has no time embedding (temb_channels=None), GroupNorm eps 1e-6, 1x1 shortcut when channels change.
+Encoder (`vae.encode(image).latent_dist.sample(generator)`, models/pipelines.py:624-626, one call per turn):
+  h    = conv_in(x)                                          (3x3, 3 -> 128)
+  down i: 2 x ResnetBlock2D (128 | 128->256 | 256->512 | 512), then F.pad(h, (0,1,0,1)) + conv3x3 stride 2 for i < 3
+  mid  : as in the decoder;  moments = quant_conv(conv_out(silu(GroupNorm(h))))   (3x3 512 -> 8, then 1x1 8 -> 8)
+  DiagonalGaussianDistribution: mean, logvar = chunk(moments, 2); logvar clamped to [-30, 20]; sample = mean + exp(0.5 logvar) * noise
 State-dict keys are diffusers' (`post_quant_conv`, `decoder.conv_in`, `decoder.mid_block.{resnets,attentions}`,
 `decoder.up_blocks.N.{resnets,upsamplers}`, `decoder.conv_norm_out`, `decoder.conv_out`; attention projections
 `to_q/to_k/to_v/to_out.0` with `group_norm`), so a real checkpoint drops in.
@@ -116,4 +121,75 @@ def synth_state_dict(seed=777, dtype=torch.float32):
         conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", UP_CHANNELS[i], UP_CHANNELS[i], 3)
     norm("decoder.conv_norm_out", 128)
     conv("decoder.conv_out", 3, 128, 3)
+    return sd
+
+
+ENC_CHANNELS = (128, 256, 512, 512)
+
+
+def enc_resnet_specs():
+    out, ch = [], 128
+    for i, co in enumerate(ENC_CHANNELS):
+        for j in range(2):
+            out.append((f"encoder.down_blocks.{i}.resnets.{j}", ch, co))
+            ch = co
+    return out + [("encoder.mid_block.resnets.0", 512, 512), ("encoder.mid_block.resnets.1", 512, 512)]
+
+
+def encode_moments(sd, x):
+    """x [B,3,512,512] in [-1, 1] -> moments [B,8,64,64] (mean | logvar before clamping)."""
+    h = _conv(x, sd, "encoder.conv_in")
+    for i in range(4):
+        for j in range(2):
+            h = resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", h)
+        if i < 3:
+            h = _conv(F.pad(h, (0, 1, 0, 1)), sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", stride=2, padding=0)
+    h = resnet_block(sd, "encoder.mid_block.resnets.0", h)
+    h = attention_block(sd, "encoder.mid_block.attentions.0", h)
+    h = resnet_block(sd, "encoder.mid_block.resnets.1", h)
+    h = _conv(F.silu(_gn(h, sd, "encoder.conv_norm_out")), sd, "encoder.conv_out")
+    return _conv(h, sd, "quant_conv", padding=0)
+
+
+def sample_posterior(moments, noise):
+    """DiagonalGaussianDistribution(moments).sample() with the noise supplied by the caller."""
+    mean, logvar = moments.chunk(2, dim=1)
+    std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+    return mean + std * noise
+
+
+def synth_encoder_state_dict(seed=778, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, out_c, in_c, k, scale=1.0):
+        sd[name + ".weight"] = (torch.randn(out_c, in_c, k, k, generator=g) * (scale / math.sqrt(in_c * k * k))).to(dtype)
+        sd[name + ".bias"] = (torch.randn(out_c, generator=g) * 0.02).to(dtype)
+
+    def lin(name, out_f, in_f, scale=1.0):
+        sd[name + ".weight"] = (torch.randn(out_f, in_f, generator=g) * (scale / math.sqrt(in_f))).to(dtype)
+        sd[name + ".bias"] = (torch.randn(out_f, generator=g) * 0.02).to(dtype)
+
+    def norm(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * torch.randn(c, generator=g)).to(dtype)
+        sd[name + ".bias"] = (0.05 * torch.randn(c, generator=g)).to(dtype)
+
+    conv("encoder.conv_in", 128, 3, 3, scale=2.0)
+    for p, cin, cout in enc_resnet_specs():
+        norm(p + ".norm1", cin)
+        conv(p + ".conv1", cout, cin, 3)
+        norm(p + ".norm2", cout)
+        conv(p + ".conv2", cout, cout, 3, scale=0.5)
+        if cin != cout:
+            conv(p + ".conv_shortcut", cout, cin, 1)
+    for i in range(3):
+        conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", ENC_CHANNELS[i], ENC_CHANNELS[i], 3)
+    a = "encoder.mid_block.attentions.0"
+    norm(a + ".group_norm", 512)
+    for n in ("to_q", "to_k", "to_v"):
+        lin(f"{a}.{n}", 512, 512, scale=2.0)
+    lin(a + ".to_out.0", 512, 512, scale=0.5)
+    norm("encoder.conv_norm_out", 512)
+    conv("encoder.conv_out", 8, 512, 3)
+    conv("quant_conv", 8, 8, 1, scale=1.5)
     return sd

@@ -183,3 +183,19 @@ def test_vae_decoder_oracle_structure():
     with torch.no_grad():
         img = OV.decode(sd, z)
     assert img.shape == (1, 3, 128, 128) and torch.isfinite(img).all()
+
+
+def test_vae_encoder_oracle_structure():
+    """encoder half: published parameter count of the SD VAE encoder (34,163,592 + 72 for quant_conv; 83,653,863 for the
+    whole AutoencoderKL), 8x downsampling with one-sided padding, posterior sampling."""
+    from oracle import vae as OV
+    sd = OV.synth_encoder_state_dict(778)
+    assert sum(v.numel() for v in sd.values()) == 34_163_664
+    assert sum(v.numel() for v in sd.values()) + sum(v.numel() for v in OV.synth_state_dict(777).values()) == 83_653_863
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 3, 64, 64, generator=g) * 2 - 1
+    with torch.no_grad():
+        m = OV.encode_moments(sd, x)
+    assert m.shape == (1, 8, 8, 8)
+    z = OV.sample_posterior(m, torch.zeros(1, 4, 8, 8))
+    assert torch.equal(z, m[:, :4])

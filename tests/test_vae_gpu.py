@@ -92,3 +92,41 @@ def test_vae_decode_timing_context():
         out[name] = (time.perf_counter() - t0) / 5 * 1e3
     print("VAE decode 512x512, ms:", {k: round(v, 2) for k, v in out.items()})
     assert out["ours"] < 2.0 * out["torch_eager_fp16"]
+
+
+def test_vae_encode_parity():
+    """Encoder moments (mean | logvar) and the posterior sample vs the oracle; one-sided padding of the stride-2 convs."""
+    from oracle import vae as OV
+    from theatergen_b200 import ops
+    from theatergen_b200.vae import TGAutoencoderKL
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {**OV.synth_state_dict(777), **OV.synth_encoder_state_dict(778)}
+    vae = TGAutoencoderKL(sd)
+    g = torch.Generator().manual_seed(21)
+    img = (torch.rand(1, 3, 512, 512, generator=g) * 2 - 1).half().cuda()
+    dist = vae.encode(img).latent_dist
+    m = dist.moments
+    assert m.shape == (1, 8, 64, 64)
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    sd16 = {k: v.half().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = OV.encode_moments(sd32, img.float())
+        ref16 = OV.encode_moments(sd16, img)
+    e, e16 = (m.float() - ref32).abs(), (ref16.float() - ref32).abs()
+    rms = lambda t: t.pow(2).mean().sqrt().item()
+    print(f"vae encode moments: max_abs {e.max().item():.3e} rel_rms {rms(e) / rms(ref32):.3e} | fp16 oracle max_abs "
+          f"{e16.max().item():.3e} rel_rms {rms(e16) / rms(ref32):.3e}")
+    assert e.max().item() <= max(1.5 * e16.max().item(), 1e-2)
+    assert rms(e) / rms(ref32) <= max(1.5 * rms(e16) / rms(ref32), 3e-3)
+    noise = torch.randn(1, 4, 64, 64, generator=g).half().cuda()
+    z = dist.sample(noise=noise)
+    zref = OV.sample_posterior(m.float(), noise.float())
+    assert (z.float() - zref).abs().max().item() < 4e-3 * max(1.0, zref.abs().max().item())
+    assert torch.equal(dist.mode(), ops.gaussian_sample(m, None)) and (dist.mode().float() - m[:, :4].float()).abs().max().item() == 0
+    # stride-2 im2col with the VAE's (0,1,0,1) padding
+    x = _rand((1, 16, 16, 64), 5)
+    a = ops.im2col_s2(x, pad_lo=0)
+    unf = F.unfold(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), 3, padding=0, stride=2)
+    unf = unf.reshape(1, 64, 9, 64).permute(0, 3, 2, 1).reshape(64, 9 * 64)
+    assert torch.equal(a.float(), unf)

@@ -29,7 +29,8 @@ _SIGS = {
     "tg_attention_tc": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_attention_cross_ip": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_upsample2x": (ci, [vp, ci, ci, ci, ci, vp, vp]),
-    "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, vp]),
+    "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
+    "tg_gaussian_sample": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
     "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_im2col_small": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "tg_conv_out": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]),

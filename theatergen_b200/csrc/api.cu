@@ -86,9 +86,14 @@ int tg_upsample2x(const tg_half* x, int B, int Hh, int W, int C, tg_half* y, voi
   TG_CHECK(x && y, "tg_upsample2x: null pointer");
   return tg::upsample2x_nhwc(H(x), B, Hh, W, C, HM(y), ST(stream));
 }
-int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, void* stream) {
+int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int pad_lo, void* stream) {
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
-  return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), ST(stream));
+  return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
+}
+int tg_gaussian_sample(const tg_half* moments, const tg_half* noise, tg_half* z, int B, int L, int HW, float out_scale,
+                       void* stream) {
+  TG_CHECK(moments && z, "tg_gaussian_sample: null pointer");
+  return tg::gaussian_sample(H(moments), H(noise), HM(z), B, L, HW, out_scale, ST(stream));
 }
 int tg_conv_in(const tg_half* x, const tg_half* w, const tg_half* bias, tg_half* y, int B, int Cin, int Hh, int W,
                int Cout, int silu, void* stream) {

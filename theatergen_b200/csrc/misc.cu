@@ -35,11 +35,12 @@ int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cuda
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// im2col for the three stride-2 3x3 convs (diffusers Downsample2D, pad 1; ip_adapter/unet_2d_blocks.py:1112,1198)
-// A[b*Ho*Wo + oy*Wo + ox][(ky*3+kx)*C + c] = x[b][2oy+ky-1][2ox+kx-1][c]  (0 outside)
+// im2col for the stride-2 3x3 convs (diffusers Downsample2D).  pad_lo = 1: symmetric padding 1 (the UNet / ControlNet,
+// ip_adapter/unet_2d_blocks.py:1112,1198); pad_lo = 0: the VAE encoder's F.pad(x, (0, 1, 0, 1)) + conv(padding=0)
+// A[b*Ho*Wo + oy*Wo + ox][(ky*3+kx)*C + c] = x[b][2oy+ky-pad_lo][2ox+kx-pad_lo][c]  (0 outside)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int H, int W, int C8, size_t total) {
+im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int H, int W, int C8, size_t total, int pad_lo) {
   grid_dep_launch();
   grid_dep_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -52,19 +53,19 @@ im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ a, int H, int 
     p /= Wo;
     const int oy = (int)(p % Ho);
     const int b = (int)(p / Ho);
-    const int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    const int iy = 2 * oy + tap / 3 - pad_lo, ix = 2 * ox + tap % 3 - pad_lo;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((size_t)b * H + iy) * W + ix) * C8 + c];
     a[i] = v;
   }
 }
 
-int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, cudaStream_t st) {
-  TG_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad dims");
+int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, int pad_lo, cudaStream_t st) {
+  TG_CHECK(C % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (pad_lo == 0 || pad_lo == 1), "im2col_s2: bad dims");
   const size_t total = (size_t)B * (H / 2) * (W / 2) * 9 * (C / 8);
-  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 16) ? ((total + 255) / 256) : (size_t)(148 * 16));
   TG_CUDA(launch_kernel(im2col_s2_kernel, dim3(grid), dim3(256), 0, st, 1, reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(a), H, W, C / 8,
-                                         total));
+                                         total, pad_lo));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
@@ -257,6 +258,34 @@ int pointwise_nchw(const __half* x, const __half* w, const __half* bias, __half*
   TG_CHECK(Cin >= 1 && Cin <= 16 && Cout >= 1 && Cout <= 16, "pointwise: Cin=%d Cout=%d (1..16)", Cin, Cout);
   const int total = B * Cout * HW;
   TG_CUDA(launch_kernel(pointwise_nchw_kernel, dim3((total + 255) / 256), dim3(256), 0, st, 1, x, w, bias, y, Cin, Cout, HW, total));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// diffusers DiagonalGaussianDistribution.sample on the VAE encoder's moments (NCHW [B, 2L, HW]: L mean channels then L
+// log-variance channels): z = (mean + exp(0.5 clamp(logvar, -30, 20)) * noise) * out_scale      (models/pipelines.py:624-626)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gaussian_sample_kernel(const __half* __restrict__ moments, const __half* __restrict__ noise, __half* __restrict__ z, int L,
+                       int HW, int total, float out_scale) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int p = i % HW, c = (i / HW) % L, b = i / (HW * L);
+    const float mean = __half2float(moments[((size_t)b * 2 * L + c) * HW + p]);
+    const float logvar = fminf(fmaxf(__half2float(moments[((size_t)b * 2 * L + L + c) * HW + p]), -30.f), 20.f);
+    // the reference computes in fp16 tensors: std and the product are rounded to fp16 like there
+    const float std_ = __half2float(__float2half_rn(expf(0.5f * logvar)));
+    const float n = noise ? __half2float(noise[i]) : 0.f;
+    z[i] = __float2half_rn(__half2float(__float2half_rn(mean + __half2float(__float2half_rn(std_ * n)))) * out_scale);
+  }
+}
+int gaussian_sample(const __half* moments, const __half* noise, __half* z, int B, int L, int HW, float out_scale,
+                    cudaStream_t st) {
+  const int total = B * L * HW;
+  TG_CUDA(launch_kernel(gaussian_sample_kernel, dim3((total + 255) / 256), dim3(256), 0, st, 1, moments, noise, z, L, HW, total, out_scale));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;

@@ -218,12 +218,25 @@ def upsample2x(x, out=None):
     return out
 
 
-def im2col_s2(x, out=None):
+def gaussian_sample(moments, noise, out_scale=1.0, out=None):
+    """moments NCHW [B,2L,H,W] (mean | logvar), noise [B,L,H,W] or None -> (mean + std * noise) * out_scale."""
+    _chk16(moments, noise, out)
+    B, L2, H, W = moments.shape
+    L = L2 // 2
+    assert moments.is_contiguous() and (noise is None or (noise.is_contiguous() and noise.shape == (B, L, H, W)))
+    if out is None:
+        out = torch.empty((B, L, H, W), dtype=torch.float16, device=moments.device)
+    _lib.check(_lib.lib().tg_gaussian_sample(_p(moments), _p(noise), _p(out), B, L, H * W, float(out_scale), _stream()),
+               "tg_gaussian_sample")
+    return out
+
+
+def im2col_s2(x, out=None, pad_lo=1):
     _chk16(x, out)
     B, H, W, Cc = x.shape
     if out is None:
         out = torch.empty((B * (H // 2) * (W // 2), 9 * Cc), dtype=torch.float16, device=x.device)
-    _lib.check(_lib.lib().tg_im2col_s2(_p(x), B, H, W, Cc, _p(out), _stream()), "tg_im2col_s2")
+    _lib.check(_lib.lib().tg_im2col_s2(_p(x), B, H, W, Cc, _p(out), int(pad_lo), _stream()), "tg_im2col_s2")
     return out
 
 
