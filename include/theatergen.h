@@ -120,6 +120,9 @@ int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg
 int tg_upsample2x(const tg_half* x, int B, int H, int W, int C, tg_half* y, void* stream);
 /* pad_lo = 1: symmetric padding 1 (UNet / ControlNet Downsample2D); pad_lo = 0: the VAE encoder's F.pad(x,(0,1,0,1)) */
 int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, int pad_lo, void* stream);
+/* non-overlapping P x P patches of an NCHW image as GEMM rows [B*(H/P)*(W/P), Kpad], column k = c*P*P + ky*P + kx (the
+ * CLIP ViT patch embedding, transformers CLIPVisionEmbeddings; ip_adapter/ip_adapter.py:78-81, 142-153) */
+int tg_im2col_patch(const tg_half* x_nchw, tg_half* out, int B, int Cin, int H, int W, int P, int Kpad, void* stream);
 /* diffusers DiagonalGaussianDistribution.sample on NCHW moments [B,2L,HW]: z = (mean + exp(0.5 clamp(logvar,-30,20)) *
  * noise) * out_scale; noise NULL = the mode (models/pipelines.py:624-626) */
 int tg_gaussian_sample(const tg_half* moments, const tg_half* noise, tg_half* z, int B, int L, int HW, float out_scale,

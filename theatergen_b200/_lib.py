@@ -30,6 +30,7 @@ _SIGS = {
     "tg_attention_cross_ip": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_upsample2x": (ci, [vp, ci, ci, ci, ci, vp, vp]),
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
+    "tg_im2col_patch": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_gaussian_sample": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
     "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_im2col_small": (ci, [vp, vp, ci, ci, ci, ci, vp]),

@@ -90,6 +90,10 @@ int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int 
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
 }
+int tg_im2col_patch(const tg_half* x, tg_half* out, int B, int Cin, int Hh, int W, int P, int Kpad, void* stream) {
+  TG_CHECK(x && out, "tg_im2col_patch: null pointer");
+  return tg::im2col_patch(H(x), HM(out), B, Cin, Hh, W, P, Kpad, ST(stream));
+}
 int tg_gaussian_sample(const tg_half* moments, const tg_half* noise, tg_half* z, int B, int L, int HW, float out_scale,
                        void* stream) {
   TG_CHECK(moments && z, "tg_gaussian_sample: null pointer");

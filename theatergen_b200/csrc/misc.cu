@@ -264,6 +264,40 @@ int pointwise_nchw(const __half* x, const __half* w, const __half* bias, __half*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Non-overlapping patch embedding as a GEMM (CLIP ViT: Conv2d(3, width, kernel = stride = P, bias = False)):
+// out[(b, py, px)][k] = x[b][c][py*P + ky][px*P + kx] with k = c*P*P + ky*P + kx (a torch [width][3][P][P] weight
+// flattened), zero for k >= Cin*P*P (K padded to a multiple of 64).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_patch_kernel(const __half* __restrict__ x, __half* __restrict__ out, int Cin, int H, int W, int P, int Kpad,
+                    size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int gw = W / P, gh = H / P, KK = Cin * P * P;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const size_t row = i / Kpad;
+    const int px = (int)(row % gw), py = (int)((row / gw) % gh);
+    const size_t b = row / ((size_t)gw * gh);
+    __half v = __float2half(0.f);
+    if (k < KK) {
+      const int c = k / (P * P), r = k - c * P * P, ky = r / P, kx = r - ky * P;
+      v = x[((b * Cin + c) * H + py * P + ky) * W + px * P + kx];
+    }
+    out[i] = v;
+  }
+}
+int im2col_patch(const __half* x, __half* out, int B, int Cin, int H, int W, int P, int Kpad, cudaStream_t st) {
+  TG_CHECK(H % P == 0 && W % P == 0 && Kpad % 64 == 0 && Kpad >= Cin * P * P, "im2col_patch: H=%d W=%d P=%d Kpad=%d", H, W, P, Kpad);
+  const size_t total = (size_t)B * (H / P) * (W / P) * Kpad;
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 16) ? ((total + 255) / 256) : (size_t)(148 * 16));
+  TG_CUDA(launch_kernel(im2col_patch_kernel, dim3(grid), dim3(256), 0, st, 1, x, out, Cin, H, W, P, Kpad, total));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // diffusers DiagonalGaussianDistribution.sample on the VAE encoder's moments (NCHW [B, 2L, HW]: L mean channels then L
 // log-variance channels): z = (mean + exp(0.5 clamp(logvar, -30, 20)) * noise) * out_scale      (models/pipelines.py:624-626)
 // ---------------------------------------------------------------------------------------------------------

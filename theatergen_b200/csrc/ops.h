@@ -56,6 +56,7 @@ int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half*
 
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, int pad_lo, cudaStream_t st);
+int im2col_patch(const __half* x, __half* out, int B, int Cin, int H, int W, int P, int Kpad, cudaStream_t st);
 int gaussian_sample(const __half* moments, const __half* noise, __half* z, int B, int L, int HW, float out_scale,
                     cudaStream_t st);
 int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int H, int W,

@@ -1,9 +1,9 @@
 """IPAdapter wrapper with the reference's surface (ip_adapter/ip_adapter.py:67-158, 289-317):
 `.pipe`, `.device`, `.set_ip_adapter()`, `.load_ip_adapter()`, `.get_image_embeds()`, `.set_scale()`.
 
-The CLIP-ViT-H image encoder in front of the projector is outside this round's scope: pass
-`image_encoder=` (any callable returning `.image_embeds` / `.hidden_states`) or call
-`get_image_embeds(clip_image_embeds=...)`, which is the branch the projector kernels serve.
+The CLIP-ViT-H image encoder in front of the projector is `theatergen_b200.clip_vision.TGCLIPVision`:
+pass it as `image_encoder=` (any callable with the transformers surface `.image_embeds` / `.hidden_states` works), or
+call `get_image_embeds(clip_image_embeds=...)` with precomputed embeddings.
 """
 from __future__ import annotations
 
@@ -119,7 +119,7 @@ class IPAdapter:
     def get_image_embeds(self, pil_image=None, clip_image_embeds=None):
         if pil_image is not None:
             if self.image_encoder is None:
-                raise RuntimeError("no image encoder bound: pass clip_image_embeds (CLIP-ViT-H is outside this build)")
+                raise RuntimeError("no image encoder bound: pass image_encoder=TGCLIPVision(...) or clip_image_embeds")
             clip_image = self.clip_image_processor(images=pil_image, return_tensors="pt").pixel_values
             clip_image_embeds = self.image_encoder(clip_image.to(self.device, dtype=torch.float16)).image_embeds
         clip_image_embeds = clip_image_embeds.to(self.device, dtype=torch.float16)
@@ -148,7 +148,7 @@ class IPAdapterPlus(IPAdapter):
         """clip_image_embeds: penultimate hidden states [n,257,1280] (hidden_states[-2], ip_adapter.py:310)."""
         if pil_image is not None:
             if self.image_encoder is None:
-                raise RuntimeError("no image encoder bound: pass clip_image_embeds (CLIP-ViT-H is outside this build)")
+                raise RuntimeError("no image encoder bound: pass image_encoder=TGCLIPVision(...) or clip_image_embeds")
             clip_image = self.clip_image_processor(images=pil_image, return_tensors="pt").pixel_values
             clip_image = clip_image.to(self.device, dtype=torch.float16)
             clip_image_embeds = self.image_encoder(clip_image, output_hidden_states=True).hidden_states[-2]

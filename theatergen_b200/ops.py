@@ -218,6 +218,16 @@ def upsample2x(x, out=None):
     return out
 
 
+def im2col_patch(x_nchw, P, Kpad):
+    """[B,Cin,H,W] -> [B*(H/P)*(W/P), Kpad] rows of flattened P x P patches (k = c*P*P + ky*P + kx, zero padded)."""
+    _chk16(x_nchw)
+    B, Cin, H, W = x_nchw.shape
+    assert x_nchw.is_contiguous()
+    out = torch.empty((B * (H // P) * (W // P), Kpad), dtype=torch.float16, device=x_nchw.device)
+    _lib.check(_lib.lib().tg_im2col_patch(_p(x_nchw), _p(out), B, Cin, H, W, P, Kpad, _stream()), "tg_im2col_patch")
+    return out
+
+
 def gaussian_sample(moments, noise, out_scale=1.0, out=None):
     """moments NCHW [B,2L,H,W] (mean | logvar), noise [B,L,H,W] or None -> (mean + std * noise) * out_scale."""
     _chk16(moments, noise, out)
