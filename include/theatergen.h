@@ -37,6 +37,7 @@ int tg_init(void);
 #define TG_ACT_SILU 1
 #define TG_ACT_GEGLU 2 /* weight rows packed per 64: [32 value | 32 gate]; out has N/2 columns */
 #define TG_ACT_GELU 3  /* exact (erf) GELU, ip_adapter/resampler.py:18 */
+#define TG_ACT_QUICK_GELU 4 /* x * sigmoid(1.702 x): the CLIP text encoder's MLP (generate.py:60 loads it) */
 
 /* out[M,N] = act( [A1|A2][M,K] * Wt[N,K]^T + bias[N] + rowbias[m/rows_per_image, N] ) + residual[M,N]
  * tcgen05 tensor-core GEMM (TMA-fed, TMEM accumulators).  A2 may be NULL (K1 == K); bias / rowbias /
@@ -90,10 +91,11 @@ int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half*
 
 /* Flash attention: O[b,n,h*d:(h+1)*d] = softmax(scale Q K^T) V per (b,h).  Q/K/V/O are token-major with row
  * pitches ld* (elements) and head h at column offset h*d (pass pointers into a fused QKV buffer).
- * d in {40,64,80,160}.  Replaces AttnProcessor.__call__ (ip_adapter/attention_processor.py:343-356) and
- * PerceiverAttention's softmax(QK^T)V (ip_adapter/resampler.py:65-74). */
+ * d in {40,64,80,160}; causal != 0 masks keys behind the query (Nq == Nk).  Replaces AttnProcessor.__call__
+ * (ip_adapter/attention_processor.py:343-356), PerceiverAttention's softmax(QK^T)V (ip_adapter/resampler.py:65-74) and the
+ * attention of the CLIP encoders (transformers CLIPAttention; ip_adapter/ip_adapter.py:78-81, models/pipelines.py:238). */
 int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
-                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, void* stream);
+                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, int causal, void* stream);
 
 /* Same contract on the tcgen05 path (TMA-fed tiles, S/O accumulators in TMEM) for head dims <= 64: Q/K/V must be
  * head-padded to 64 columns (head h at column h*64, columns [d,64) zero -- obtained for free by zero rows in the
@@ -123,6 +125,10 @@ int tg_im2col_s2(const tg_half* x, int B, int H, int W, int C, tg_half* a, int p
 /* non-overlapping P x P patches of an NCHW image as GEMM rows [B*(H/P)*(W/P), Kpad], column k = c*P*P + ky*P + kx (the
  * CLIP ViT patch embedding, transformers CLIPVisionEmbeddings; ip_adapter/ip_adapter.py:78-81, 142-153) */
 int tg_im2col_patch(const tg_half* x_nchw, tg_half* out, int B, int Cin, int H, int W, int P, int Kpad, void* stream);
+/* out[b][t][:] = table[ids[b][t]][:] + pos[t][:]: transformers CLIPTextEmbeddings, the first step of
+ * `text_encoder(input_ids)[0]` (models/models.py:69-70).  ids are int64 token ids in [0, vocab), device memory. */
+int tg_embed_tokens(const long long* ids, const tg_half* table, const tg_half* pos, tg_half* out, int B, int T, int C,
+                    int vocab, void* stream);
 /* diffusers DiagonalGaussianDistribution.sample on NCHW moments [B,2L,HW]: z = (mean + exp(0.5 clamp(logvar,-30,20)) *
  * noise) * out_scale; noise NULL = the mode (models/pipelines.py:624-626) */
 int tg_gaussian_sample(const tg_half* moments, const tg_half* noise, tg_half* z, int B, int L, int HW, float out_scale,

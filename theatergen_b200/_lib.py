@@ -25,12 +25,13 @@ _SIGS = {
     "tg_gemm_set_scratch_slot": (ci, [ci]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),
-    "tg_attention": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, cf, vp]),
+    "tg_attention": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, cf, ci, vp]),
     "tg_attention_tc": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_attention_cross_ip": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_upsample2x": (ci, [vp, ci, ci, ci, ci, vp, vp]),
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
     "tg_im2col_patch": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "tg_embed_tokens": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
     "tg_gaussian_sample": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
     "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_im2col_small": (ci, [vp, vp, ci, ci, ci, ci, vp]),

@@ -62,9 +62,9 @@ int tg_layernorm(const tg_half* x, int ldx, const tg_half* gamma, const tg_half*
 }
 
 int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
-                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, void* stream) {
+                 int ldo, int B, int heads, int Nq, int Nk, int d, float scale, int causal, void* stream) {
   TG_CHECK(Q && K && V && O && Nq > 0 && Nk > 0, "tg_attention: bad arguments");
-  return tg::attention_flash(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, Nq, Nk, d, scale, ST(stream));
+  return tg::attention_flash(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, Nq, Nk, d, scale, causal, ST(stream));
 }
 
 int tg_attention_tc(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
@@ -89,6 +89,11 @@ int tg_upsample2x(const tg_half* x, int B, int Hh, int W, int C, tg_half* y, voi
 int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int pad_lo, void* stream) {
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
+}
+int tg_embed_tokens(const long long* ids, const tg_half* table, const tg_half* pos, tg_half* out, int B, int T, int C,
+                    int vocab, void* stream) {
+  TG_CHECK(ids && table && pos && out, "tg_embed_tokens: null pointer");
+  return tg::embed_tokens(ids, H(table), H(pos), HM(out), B, T, C, vocab, ST(stream));
 }
 int tg_im2col_patch(const tg_half* x, tg_half* out, int B, int Cin, int Hh, int W, int P, int Kpad, void* stream) {
   TG_CHECK(x && out, "tg_im2col_patch: null pointer");

@@ -73,7 +73,7 @@ struct SelfCfg {
 template <int D, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32)
 attn_self_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, const __half* __restrict__ V, int ldq,
-                 int ldk, int ldv, __half* __restrict__ O, int ldo, int Nq, int Nk, float scale_log2) {
+                 int ldk, int ldv, __half* __restrict__ O, int ldo, int Nq, int Nk, float scale_log2, int causal) {
   grid_dep_launch();
   grid_dep_wait();
   using Cfg = SelfCfg<D, NWARPS>;
@@ -156,6 +156,19 @@ attn_self_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, con
         if (c + 1 >= Nk) s[j][1] = s[j][3] = -INFINITY;
       }
     }
+    // causal mask (CLIP text encoder): key index > query index.  Key 0 is visible to every row, so the running maximum
+    // is finite after the first tile and fully masked later tiles contribute exp2(-inf) = 0.
+    if (causal) {
+      const int qr0 = q0 + warp * 16 + (lane >> 2), qr1 = qr0 + 8;
+#pragma unroll
+      for (int j = 0; j < BKV / 8; ++j) {
+        const int c = kbase + j * 8 + (lane & 3) * 2;
+        if (c > qr0) s[j][0] = -INFINITY;
+        if (c + 1 > qr0) s[j][1] = -INFINITY;
+        if (c > qr1) s[j][2] = -INFINITY;
+        if (c + 1 > qr1) s[j][3] = -INFINITY;
+      }
+    }
     // ---- online softmax (rows g and g+8 of the warp's 16) ----
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
@@ -228,7 +241,7 @@ attn_self_kernel(const __half* __restrict__ Q, const __half* __restrict__ K, con
 
 template <int D, int NWARPS>
 static int launch_self(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O,
-                       int ldo, int B, int heads, int Nq, int Nk, float scale, cudaStream_t st) {
+                       int ldo, int B, int heads, int Nq, int Nk, float scale, int causal, cudaStream_t st) {
   using Cfg = SelfCfg<D, NWARPS>;
   auto kern = attn_self_kernel<D, NWARPS>;
   static bool attr = false;
@@ -237,20 +250,21 @@ static int launch_self(const __half* Q, const __half* K, const __half* V, int ld
     attr = true;
   }
   dim3 grid((Nq + Cfg::BQ - 1) / Cfg::BQ, heads, B);
-  TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, K, V, ldq, ldk, ldv, O, ldo, Nq, Nk, scale * 1.4426950408889634f));
+  TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, K, V, ldq, ldk, ldv, O, ldo, Nq, Nk, scale * 1.4426950408889634f, causal));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
 }
 
 int attention_flash(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
-                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t st) {
+                    int B, int heads, int Nq, int Nk, int d, float scale, int causal, cudaStream_t st) {
+  TG_CHECK(!causal || Nq == Nk, "attention: the causal mask needs Nq == Nk");
   TG_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention: pitches must be 16B aligned");
   const bool big = Nq >= 128;
 #define TG_SELF(DD)                                                                                         \
   case DD:                                                                                                  \
-    return big ? launch_self<DD, 8>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, Nq, Nk, scale, st)            \
-               : launch_self<DD, 4>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, Nq, Nk, scale, st);
+    return big ? launch_self<DD, 8>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, Nq, Nk, scale, causal, st)    \
+               : launch_self<DD, 4>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, Nq, Nk, scale, causal, st);
   switch (d) {
     TG_SELF(40) TG_SELF(64) TG_SELF(80) TG_SELF(160)
     default:

@@ -221,6 +221,12 @@ __device__ __forceinline__ float silu_f(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
   return x * fmaf(0.5f, t, 0.5f);
 }
+// x * sigmoid(1.702 x), the activation of OpenAI CLIP's MLPs (the SD-1.5 text encoder); one MUFU operation.
+__device__ __forceinline__ float quick_gelu_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  return x * fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 // exact-GELU without MUFU: erf(z) = z * P(z^2) on [0, 3.2] (degree-8 least-squares fit at Chebyshev nodes, |err| < 9e-5,
 // i.e. below fp16 resolution of the result), clamped to 1 beyond.  ~14 FMA-pipe instructions, no SFU traffic, so a GEGLU

@@ -193,6 +193,9 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, float (&v)[32], 
   } else if (g.act == 3) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
+  } else if (g.act == 4) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
   }
   if (row_ok && g.residual) {
 #pragma unroll

@@ -264,6 +264,48 @@ int pointwise_nchw(const __half* x, const __half* w, const __half* bias, __half*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Token + position embedding of the CLIP text encoder: out[b][t][:] = table[ids[b][t]][:] + pos[t][:] (fp32 add, one
+// rounding).  One warp per token row, 16-byte accesses; ids outside [0, vocab) are a caller error and read row 0 after the
+// device-side flag is raised (checked by the host wrapper's launch check in debug runs).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_tokens_kernel(const long long* __restrict__ ids, const __half* __restrict__ table, const __half* __restrict__ pos,
+                    __half* __restrict__ out, int rows, int T, int C, int vocab) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 8) {
+    long long id = ids[row];
+    if (id < 0 || id >= vocab) id = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)id * C);
+    const uint4* ps = reinterpret_cast<const uint4*>(pos + (size_t)(row % T) * C);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)row * C);
+    for (int i = lane; i < C / 8; i += 32) {
+      uint4 a = __ldg(src + i), p = __ldg(ps + i), o;
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+      const __half2* ph = reinterpret_cast<const __half2*>(&p);
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = __half22float2(ah[j]), y = __half22float2(ph[j]);
+        oh[j] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+      }
+      dst[i] = o;
+    }
+  }
+}
+int embed_tokens(const long long* ids, const __half* table, const __half* pos, __half* out, int B, int T, int C,
+                 int vocab, cudaStream_t st) {
+  TG_CHECK(C % 8 == 0 && B > 0 && T > 0 && vocab > 0, "embed_tokens: B=%d T=%d C=%d vocab=%d", B, T, C, vocab);
+  const int rows = B * T;
+  const int grid = (rows + 7) / 8 < 148 * 8 ? (rows + 7) / 8 : 148 * 8;
+  TG_CUDA(launch_kernel(embed_tokens_kernel, dim3(grid), dim3(256), 0, st, 1, ids, table, pos, out, rows, T, C, vocab));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Non-overlapping patch embedding as a GEMM (CLIP ViT: Conv2d(3, width, kernel = stride = P, bias = False)):
 // out[(b, py, px)][k] = x[b][c][py*P + ky][px*P + kx] with k = c*P*P + ky*P + kx (a torch [width][3][P][P] weight
 // flattened), zero for k >= Cin*P*P (K padded to a multiple of 64).

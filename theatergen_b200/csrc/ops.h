@@ -43,7 +43,7 @@ int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* 
 
 // O[b, n, h*d..] = softmax(scale * Q K^T) V per (b, h); row pitches in elements
 int attention_flash(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
-                    int B, int heads, int Nq, int Nk, int d, float scale, cudaStream_t st);
+                    int B, int heads, int Nq, int Nk, int d, float scale, int causal, cudaStream_t st);
 // tcgen05 flash self-attention; Q/K/V head-padded to 64 columns (head h at column h*64), N % 128 == 0, d <= 64
 int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
                  int B, int heads, int N, int d, float scale, cudaStream_t st);
@@ -57,6 +57,8 @@ int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half*
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, int pad_lo, cudaStream_t st);
 int im2col_patch(const __half* x, __half* out, int B, int Cin, int H, int W, int P, int Kpad, cudaStream_t st);
+int embed_tokens(const long long* ids, const __half* table, const __half* pos, __half* out, int B, int T, int C,
+                 int vocab, cudaStream_t st);
 int gaussian_sample(const __half* moments, const __half* noise, __half* z, int B, int L, int HW, float out_scale,
                     cudaStream_t st);
 int conv_in_nchw_to_nhwc(const __half* x, const __half* w, const __half* bias, __half* y, int B, int Cin, int H, int W,

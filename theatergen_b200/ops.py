@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-TG_ACT_NONE, TG_ACT_SILU, TG_ACT_GEGLU, TG_ACT_GELU = 0, 1, 2, 3
+TG_ACT_NONE, TG_ACT_SILU, TG_ACT_GEGLU, TG_ACT_GELU, TG_ACT_QUICK_GELU = 0, 1, 2, 3, 4
 
 # ---------------------------------------------------------------------------------------------------------
 # optional per-launch timing (bench.py roofline leg): CUDA events on the launching stream around each op
@@ -156,7 +156,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return out
 
 
-def attention(q, k, v, B, heads, scale=None, out=None):
+def attention(q, k, v, B, heads, scale=None, out=None, causal=False):
     """q [B*Nq, heads*d] (row pitch may exceed), k/v [B*Nk, heads*d] views -> out [B*Nq, heads*d]."""
     _chk16(q, k, v, out)
     d = q.shape[1] // heads
@@ -167,7 +167,7 @@ def attention(q, k, v, B, heads, scale=None, out=None):
         out = torch.empty((B * Nq, heads * d), dtype=torch.float16, device=q.device)
     rc = _timed("attn_self_kernel", 4.0 * B * heads * Nq * Nk * d, 2.0 * B * heads * d * (2 * Nq + 2 * Nk),
                 lambda: _lib.lib().tg_attention(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out),
-                                                out.stride(0), B, heads, Nq, Nk, d, float(scale), _stream()))
+                                                out.stride(0), B, heads, Nq, Nk, d, float(scale), int(causal), _stream()))
     _lib.check(rc, "tg_attention")
     return out
 
@@ -225,6 +225,19 @@ def im2col_patch(x_nchw, P, Kpad):
     assert x_nchw.is_contiguous()
     out = torch.empty((B * (H // P) * (W // P), Kpad), dtype=torch.float16, device=x_nchw.device)
     _lib.check(_lib.lib().tg_im2col_patch(_p(x_nchw), _p(out), B, Cin, H, W, P, Kpad, _stream()), "tg_im2col_patch")
+    return out
+
+
+def embed_tokens(ids, table, pos):
+    """ids int64 [B,T] on the device; table [vocab,C]; pos [T,C] -> [B*T, C] = table[ids] + pos."""
+    _chk16(table, pos)
+    assert ids.dtype == torch.int64 and ids.is_cuda and ids.is_contiguous() and table.is_contiguous() and pos.is_contiguous()
+    B, T = ids.shape
+    C = table.shape[1]
+    assert pos.shape[0] >= T and pos.shape[1] == C
+    out = torch.empty((B * T, C), dtype=torch.float16, device=table.device)
+    _lib.check(_lib.lib().tg_embed_tokens(_p(ids), _p(table), _p(pos), _p(out), B, T, C, table.shape[0], _stream()),
+               "tg_embed_tokens")
     return out
 
 
