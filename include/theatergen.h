@@ -187,6 +187,36 @@ int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const 
                        float fg_weight, float bg_weight, float grad_scale, float ref_eps, float* loss_out,
                        float* workspace, void* stream);
 
+/* ---- input gradients of the guidance step: `torch.autograd.grad(loss, [latents])` of latent_backward_guidance
+ * (models/pipelines.py:62-128, :102).  The weights are frozen, so GEMM / convolution backward is tg_gemm / tg_conv3x3 on
+ * transposed / rotated weight copies; these entry points are the remaining operator backwards.  fp16 tensors, fp32 math. */
+/* LayerNorm: dx = rstd (dy gamma - mean(dy gamma) - xhat mean(dy gamma xhat))  (ip_adapter/attention.py:121,142,158) */
+int tg_layernorm_bwd(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* dy, int lddy, tg_half* dx, int lddx,
+                     int M, int C, float eps, void* stream);
+/* GroupNorm(32) (+SiLU when silu != 0) over channels-last [B,HW,C] (diffusers ResnetBlock2D / Transformer2DModel norms) */
+int tg_groupnorm_bwd(const tg_half* x, const tg_half* gamma, const tg_half* beta, const tg_half* dy, tg_half* dx, int B,
+                     int HW, int C, float eps, int silu, void* stream);
+/* dS = scale P o (dP - rowsum(P o dP)), P = softmax(scale S) [M,N]; ds may alias dp (AttnProcessor's softmax,
+ * ip_adapter/attention_processor.py:211-217) */
+int tg_softmax_bwd_rows(const tg_half* p, int ldp, const tg_half* dp, int lddp, tg_half* ds, int ldds, int M, int N,
+                        float scale, void* stream);
+/* GEGLU on the packed pre-activation [M,2F] (per 64 columns: 32 value | 32 gate, bias included), dy [M,F] -> dpre [M,2F] */
+int tg_geglu_bwd(const tg_half* pre, const tg_half* dy, tg_half* dpre, int M, int F, void* stream);
+/* Query gradient of tg_attention_cross_ip for ONE image (keys / values are constants of the context): dprobs (nullable,
+ * [heads,Nq,n_text]) is the energy's gradient on the captured text probabilities (tg_guidance_energy's dmaps) */
+int tg_attention_cross_ip_bwd_q(const tg_half* q, int ldq, const tg_half* kt, const tg_half* vt, const tg_half* ki,
+                                const tg_half* vi, int ldkv, int n_text, int n_ip, float ip_scale, const tg_half* dout,
+                                int lddo, const tg_half* dprobs, tg_half* dq, int lddq, int Nq, int heads, int d,
+                                float alpha, void* stream);
+/* nearest-x2 upsampling: dx [B,H,W,C] = 2x2 block sums of dy [B,2H,2W,C] */
+int tg_upsample2x_bwd(const tg_half* dy, int B, int H, int W, int C, tg_half* dx, void* stream);
+/* backward of tg_im2col_s2 (pad_lo = 1): dcols [B*(H/2)*(W/2), 9C] -> dx [B,H,W,C] */
+int tg_col2im_s2(const tg_half* dcols, int B, int H, int W, int C, tg_half* dx, void* stream);
+/* latents -= (grad * inv_scale) * step in fp32 (models/pipelines.py:106-115); grad_out (nullable, float[n]) receives the
+ * unscaled gradient; *bad (nullable, device int) is set when a gradient value is not finite (that element is skipped) */
+int tg_guidance_update(tg_half* latents, const tg_half* grad, float inv_scale, float step, float* grad_out, int* bad,
+                       int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

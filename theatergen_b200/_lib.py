@@ -32,6 +32,14 @@ _SIGS = {
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
     "tg_im2col_patch": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_embed_tokens": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_layernorm_bwd": (ci, [vp, ci, vp, vp, ci, vp, ci, ci, ci, cf, vp]),
+    "tg_groupnorm_bwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, cf, ci, vp]),
+    "tg_softmax_bwd_rows": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, cf, vp]),
+    "tg_geglu_bwd": (ci, [vp, vp, vp, ci, ci, vp]),
+    "tg_attention_cross_ip_bwd_q": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, cf, vp, ci, vp, vp, ci, ci, ci, ci, cf, vp]),
+    "tg_upsample2x_bwd": (ci, [vp, ci, ci, ci, ci, vp, vp]),
+    "tg_col2im_s2": (ci, [vp, ci, ci, ci, ci, vp, vp]),
+    "tg_guidance_update": (ci, [vp, vp, cf, cf, vp, vp, ci, vp]),
     "tg_gaussian_sample": (ci, [vp, vp, vp, ci, ci, ci, cf, vp]),
     "tg_conv_in": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_im2col_small": (ci, [vp, vp, ci, ci, ci, ci, vp]),

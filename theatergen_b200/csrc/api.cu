@@ -90,6 +90,46 @@ int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int 
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
 }
+int tg_layernorm_bwd(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* dy, int lddy, tg_half* dx, int lddx,
+                     int M, int C, float eps, void* stream) {
+  TG_CHECK(x && gamma && dy && dx, "tg_layernorm_bwd: null pointer");
+  return tg::layernorm_bwd(H(x), ldx, H(gamma), H(dy), lddy, HM(dx), lddx, M, C, eps, ST(stream));
+}
+int tg_groupnorm_bwd(const tg_half* x, const tg_half* gamma, const tg_half* beta, const tg_half* dy, tg_half* dx, int B,
+                     int HW, int C, float eps, int silu, void* stream) {
+  TG_CHECK(x && gamma && beta && dy && dx, "tg_groupnorm_bwd: null pointer");
+  return tg::groupnorm_bwd(H(x), H(gamma), H(beta), H(dy), HM(dx), B, HW, C, eps, silu, ST(stream));
+}
+int tg_softmax_bwd_rows(const tg_half* p, int ldp, const tg_half* dp, int lddp, tg_half* ds, int ldds, int M, int N,
+                        float scale, void* stream) {
+  TG_CHECK(p && dp && ds, "tg_softmax_bwd_rows: null pointer");
+  return tg::softmax_bwd_rows(H(p), ldp, H(dp), lddp, HM(ds), ldds, M, N, scale, ST(stream));
+}
+int tg_geglu_bwd(const tg_half* pre, const tg_half* dy, tg_half* dpre, int M, int F, void* stream) {
+  TG_CHECK(pre && dy && dpre, "tg_geglu_bwd: null pointer");
+  return tg::geglu_bwd(H(pre), H(dy), HM(dpre), M, F, ST(stream));
+}
+int tg_attention_cross_ip_bwd_q(const tg_half* q, int ldq, const tg_half* kt, const tg_half* vt, const tg_half* ki,
+                                const tg_half* vi, int ldkv, int n_text, int n_ip, float ip_scale, const tg_half* dout,
+                                int lddo, const tg_half* dprobs, tg_half* dq, int lddq, int Nq, int heads, int d,
+                                float alpha, void* stream) {
+  TG_CHECK(q && kt && vt && dout && dq, "tg_attention_cross_ip_bwd_q: null pointer");
+  return tg::cross_ip_bwd_q(H(q), ldq, H(kt), H(vt), H(ki), H(vi), ldkv, n_text, n_ip, ip_scale, H(dout), lddo, H(dprobs),
+                            HM(dq), lddq, Nq, heads, d, alpha, ST(stream));
+}
+int tg_upsample2x_bwd(const tg_half* dy, int B, int Hh, int W, int C, tg_half* dx, void* stream) {
+  TG_CHECK(dy && dx, "tg_upsample2x_bwd: null pointer");
+  return tg::upsample2x_bwd(H(dy), B, Hh, W, C, HM(dx), ST(stream));
+}
+int tg_col2im_s2(const tg_half* dcols, int B, int Hh, int W, int C, tg_half* dx, void* stream) {
+  TG_CHECK(dcols && dx, "tg_col2im_s2: null pointer");
+  return tg::col2im_s2(H(dcols), B, Hh, W, C, HM(dx), ST(stream));
+}
+int tg_guidance_update(tg_half* latents, const tg_half* grad, float inv_scale, float step, float* grad_out, int* bad,
+                       int n, void* stream) {
+  TG_CHECK(latents && grad, "tg_guidance_update: null pointer");
+  return tg::guidance_update(HM(latents), H(grad), inv_scale, step, grad_out, bad, n, ST(stream));
+}
 int tg_embed_tokens(const long long* ids, const tg_half* table, const tg_half* pos, tg_half* out, int B, int T, int C,
                     int vocab, void* stream) {
   TG_CHECK(ids && table && pos && out, "tg_embed_tokens: null pointer");

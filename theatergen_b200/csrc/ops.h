@@ -57,6 +57,21 @@ int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half*
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, int pad_lo, cudaStream_t st);
 int im2col_patch(const __half* x, __half* out, int B, int Cin, int H, int W, int P, int Kpad, cudaStream_t st);
+// backward.cu: input gradients of the guidance step (models/pipelines.py:62-128)
+int layernorm_bwd(const __half* x, int ldx, const __half* gamma, const __half* dy, int lddy, __half* dx, int lddx, int M,
+                  int C, float eps, cudaStream_t st);
+int groupnorm_bwd(const __half* x, const __half* gamma, const __half* beta, const __half* dy, __half* dx, int B, int HW,
+                  int C, float eps, int silu, cudaStream_t st);
+int softmax_bwd_rows(const __half* p, int ldp, const __half* dp, int lddp, __half* ds, int ldds, int M, int N,
+                     float scale, cudaStream_t st);
+int geglu_bwd(const __half* pre, const __half* dy, __half* dpre, int M, int F, cudaStream_t st);
+int cross_ip_bwd_q(const __half* q, int ldq, const __half* kt, const __half* vt, const __half* ki, const __half* vi,
+                   int ldkv, int n_text, int n_ip, float ip_scale, const __half* dout, int lddo, const __half* dprobs,
+                   __half* dq, int lddq, int Nq, int heads, int d, float alpha, cudaStream_t st);
+int upsample2x_bwd(const __half* dy, int B, int H, int W, int C, __half* dx, cudaStream_t st);
+int col2im_s2(const __half* dcols, int B, int H, int W, int C, __half* dx, cudaStream_t st);
+int guidance_update(__half* latents, const __half* grad, float inv_scale, float step, float* grad_out, int* bad, int n,
+                    cudaStream_t st);
 int embed_tokens(const long long* ids, const __half* table, const __half* pos, __half* out, int B, int T, int C,
                  int vocab, cudaStream_t st);
 int gaussian_sample(const __half* moments, const __half* noise, __half* z, int B, int L, int HW, float out_scale,

@@ -377,3 +377,88 @@ def cfg_ddim_composite(eps, latents, coef_dev, frozen=None, mask=None, latents_c
                                           Cc, H * W, _p(latents_copy), K, _stream())
     _lib.check(rc, "tg_cfg_ddim_composite")
     return latents
+
+
+# ---------------------------------------------------------------------------------------------------------
+# input-gradient operators of the guidance step (backward.cu)
+# ---------------------------------------------------------------------------------------------------------
+def layernorm_bwd(x, gamma, dy, eps=1e-5):
+    _chk16(x, gamma, dy)
+    M, Cc = x.shape
+    dx = torch.empty((M, Cc), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().tg_layernorm_bwd(_p(x), x.stride(0), _p(gamma), _p(dy), dy.stride(0), _p(dx), Cc, M, Cc,
+                                           float(eps), _stream()), "tg_layernorm_bwd")
+    return dx
+
+
+def groupnorm_bwd(x, gamma, beta, dy, eps, silu):
+    """x, dy [B,HW,C] contiguous -> dx [B,HW,C]"""
+    _chk16(x, gamma, beta, dy)
+    B, HW, Cc = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty_like(x)
+    _lib.check(_lib.lib().tg_groupnorm_bwd(_p(x), _p(gamma), _p(beta), _p(dy), _p(dx), B, HW, Cc, float(eps), int(silu),
+                                           _stream()), "tg_groupnorm_bwd")
+    return dx
+
+
+def softmax_bwd_rows(p, dp, scale, out=None):
+    """dS = scale * P o (dP - rowsum(P o dP)); writes into `out` (default: in place over dp)."""
+    _chk16(p, dp, out)
+    M, N = p.shape
+    out = dp if out is None else out
+    _lib.check(_lib.lib().tg_softmax_bwd_rows(_p(p), p.stride(0), _p(dp), dp.stride(0), _p(out), out.stride(0), M, N,
+                                              float(scale), _stream()), "tg_softmax_bwd_rows")
+    return out
+
+
+def geglu_bwd(pre, dy):
+    _chk16(pre, dy)
+    M, F2 = pre.shape
+    assert pre.is_contiguous() and dy.is_contiguous() and dy.shape == (M, F2 // 2)
+    dpre = torch.empty_like(pre)
+    _lib.check(_lib.lib().tg_geglu_bwd(_p(pre), _p(dy), _p(dpre), M, F2 // 2, _stream()), "tg_geglu_bwd")
+    return dpre
+
+
+def attention_cross_ip_bwd_q(q, kt, vt, ki, vi, heads, n_text, n_ip, ip_scale, dout, dprobs=None):
+    """One image: q/dout [Nq,C]; kt/vt/ki/vi column views [n_text+n_ip, C] of the context projection; dprobs
+    [heads,Nq,n_text] or None -> dq [Nq,C]."""
+    _chk16(q, kt, vt, ki, vi, dout, dprobs)
+    Nq, Cc = q.shape
+    d = Cc // heads
+    assert kt.stride(0) == vt.stride(0) and (ki is None or ki.stride(0) == kt.stride(0) == vi.stride(0))
+    assert dprobs is None or (dprobs.is_contiguous() and dprobs.shape == (heads, Nq, n_text))
+    dq = torch.empty((Nq, Cc), dtype=torch.float16, device=q.device)
+    _lib.check(_lib.lib().tg_attention_cross_ip_bwd_q(_p(q), q.stride(0), _p(kt), _p(vt), _p(ki), _p(vi), kt.stride(0),
+                                                      n_text, n_ip if ki is not None else 0, float(ip_scale), _p(dout),
+                                                      dout.stride(0), _p(dprobs), _p(dq), Cc, Nq, heads, d,
+                                                      float(d ** -0.5), _stream()), "tg_attention_cross_ip_bwd_q")
+    return dq
+
+
+def upsample2x_bwd(dy):
+    _chk16(dy)
+    B, H2, W2, Cc = dy.shape
+    assert dy.is_contiguous()
+    dx = torch.empty((B, H2 // 2, W2 // 2, Cc), dtype=torch.float16, device=dy.device)
+    _lib.check(_lib.lib().tg_upsample2x_bwd(_p(dy), B, H2 // 2, W2 // 2, Cc, _p(dx), _stream()), "tg_upsample2x_bwd")
+    return dx
+
+
+def col2im_s2(dcols, B, H, W, Cc):
+    _chk16(dcols)
+    assert dcols.is_contiguous() and dcols.shape == (B * (H // 2) * (W // 2), 9 * Cc)
+    dx = torch.empty((B, H, W, Cc), dtype=torch.float16, device=dcols.device)
+    _lib.check(_lib.lib().tg_col2im_s2(_p(dcols), B, H, W, Cc, _p(dx), _stream()), "tg_col2im_s2")
+    return dx
+
+
+def guidance_update(latents, grad, inv_scale, step, grad_out=None, bad=None):
+    _chk16(latents, grad)
+    assert latents.is_contiguous() and grad.is_contiguous() and latents.numel() == grad.numel()
+    assert grad_out is None or (grad_out.dtype == torch.float32 and grad_out.numel() == grad.numel())
+    assert bad is None or bad.dtype == torch.int32
+    _lib.check(_lib.lib().tg_guidance_update(_p(latents), _p(grad), float(inv_scale), float(step), _p(grad_out), _p(bad),
+                                             latents.numel(), _stream()), "tg_guidance_update")
+    return latents

@@ -18,3 +18,9 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 def pack_conv3x3(w: torch.Tensor):
     """[Cout, Cin, 3, 3] (torch) -> [Cout, 3, 3, Cin] (K ordered tap-major, channel-minor)."""
     return w.permute(0, 2, 3, 1).contiguous()
+
+
+def pack_conv3x3_dgrad(w: torch.Tensor):
+    """[Cout, Cin, 3, 3] (torch) -> the packed weight of the INPUT-gradient convolution, [Cin, 3, 3, Cout] with the taps
+    rotated by 180 degrees: dx = conv3x3(dy, this) for y = conv3x3(x, w) (stride 1, pad 1)."""
+    return w.flip(2, 3).permute(1, 2, 3, 0).contiguous()
