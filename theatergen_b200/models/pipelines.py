@@ -20,6 +20,7 @@ import warnings
 import numpy as np
 import torch
 
+from .. import ops
 from ..controlnet import TGControlNet
 from ..engine import DenoiseEngine
 from ..unet import TGUNet
@@ -64,32 +65,43 @@ def latent_backward_guidance(adapter, scheduler, unet, cond_embeddings, index, b
                              loss, loss_scale=30, loss_threshold=0.2, max_iter=5, max_index_step=10,
                              cross_attention_kwargs=None, ref_ca_saved_attns=None, guidance_attn_keys=None,
                              verbose=False, clear_cache=False, prompt_embeds=None, final=False, **kwargs):
-    """Energy side of pipelines.py:62-128 on our kernels.  The reference differentiates the energy through the whole
-    UNet with autograd (:102); this build has no UNet backward kernels, and the function has no caller in the
-    reference (SURVEY.md finding 5).  What runs here: the conditional UNet forward with in-kernel capture of the
-    guidance maps and the fused energy kernel, i.e. the loop's loss evaluation.  If an update would be required
-    (loss above threshold) a NotImplementedError is raised instead of silently skipping the gradient step."""
+    """pipelines.py:62-128 on our kernels: while the energy is above the threshold, run the conditional UNet forward with
+    in-kernel capture of the guidance maps, the fused energy kernel, and d(energy * loss_scale)/d(latents) through the
+    recorded forward (theatergen_b200/backward.py -- the reference uses autograd, :102), then
+    `latents -= grad * sqrt(1 - alpha_prod_t)` (:106-115, the DDIM branch: the scheduler has no `sigmas`).
+    Returns (latents, loss) like the reference; `loss` is a 0-d float32 CUDA tensor (energy * loss_scale)."""
+    from ..backward import GuidanceBackward
     iteration = 0
     if index < max_index_step:
         if isinstance(max_iter, list):
             max_iter = max_iter[index] if len(max_iter) > index else max_iter[-1]
+        if not isinstance(unet, TGUNet):
+            raise RuntimeError("latent_backward_guidance needs the kernel-path UNet (TGUNet)")
+        gb = getattr(unet, "_guidance_backward", None)
+        if gb is None:
+            gb = unet._guidance_backward = GuidanceBackward(unet)
+        keys = guidance_attn_keys if guidance_attn_keys is not None else DEFAULT_GUIDANCE_ATTN_KEYS
+        owned = False
+        bad = torch.zeros(1, dtype=torch.int32, device=latents.device)
         while loss.item() / loss_scale > loss_threshold and iteration < max_iter and index < max_index_step:
-            saved_attn = {}
-            kw = {"save_attn_to_dict": saved_attn, "save_keys": guidance_attn_keys}
-            if cross_attention_kwargs is not None:
-                kw.update(cross_attention_kwargs)
-            unet(scheduler.scale_model_input(latents, t), t, encoder_hidden_states=cond_embeddings,
-                 cross_attention_kwargs=kw)
-            loss = guidance.compute_ca_lossv3(saved_attn=saved_attn, bboxes=bboxes, object_positions=object_positions,
-                                              guidance_attn_keys=guidance_attn_keys,
-                                              ref_ca_saved_attns=ref_ca_saved_attns, index=index, verbose=verbose,
-                                              **kwargs) * loss_scale
+            if len(bboxes) == 0:
+                break
+            plan, ref_maps = guidance.build_plan(bboxes, object_positions, keys, ref_ca_saved_attns=ref_ca_saved_attns,
+                                                 index=index, **kwargs)
+            loss, grad = gb.energy_and_grad(scheduler.scale_model_input(latents, t), t, cond_embeddings, plan,
+                                            loss_scale=loss_scale, ref_maps=ref_maps)
             if torch.isnan(loss):
                 print("**Loss is NaN**")
-            raise NotImplementedError(
-                f"latent_backward_guidance: energy {loss.item() / loss_scale:.3f} > threshold {loss_threshold}; the "
-                "gradient step needs d(energy)/d(latents) through the UNet, which has no CUDA backward in this build "
-                "(the reference never calls this function)")
+            if not owned:  # the reference rebinds `latents` (out of place); the caller's tensor stays untouched
+                latents, owned = latents.to(torch.float16).clone(), True
+            alpha_prod_t = float(scheduler.alphas_cumprod[int(t)])
+            ops.guidance_update(latents, grad, 1.0 / gb.grad_scale, (1.0 - alpha_prod_t) ** 0.5, bad=bad)
+            iteration += 1
+            if verbose:
+                print(f"time index {index}, loss: {loss.item() / loss_scale:.3f} (de-scaled with scale {loss_scale:.1f}), "
+                      f"iteration {iteration}")
+        if int(bad):
+            warnings.warn("latent_backward_guidance: non-finite gradient values were skipped (fp16 overflow)")
     return latents, loss
 
 

@@ -100,13 +100,9 @@ def _cond_map(t):
     return t.to(torch.float16).contiguous()
 
 
-def compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, ref_ca_saved_attns=None,
-                      ref_ca_last_token_only=True, ref_ca_word_token_only=False, word_token_indices=None, index=None,
-                      ref_ca_loss_weight=1.0, verbose=False, **kwargs):
-    """Same contract as utils/guidance.py:244-286; returns a 0-d float32 CUDA tensor."""
-    dev = torch.device("cuda")
-    if len(bboxes) == 0:
-        return torch.zeros((), dtype=torch.float32, device=dev)
+def build_plan(bboxes, object_positions, guidance_attn_keys, ref_ca_saved_attns=None, ref_ca_last_token_only=True,
+               ref_ca_word_token_only=False, word_token_indices=None, index=None, ref_ca_loss_weight=1.0, **kwargs):
+    """The python description of one energy evaluation (utils/guidance.py:244-286) -> (EnergyPlan, reference maps)."""
     keys = [tuple(k) for k in guidance_attn_keys]
     ref_positions = None
     if ref_ca_saved_attns is not None and ref_ca_loss_weight != 0.0:
@@ -116,9 +112,9 @@ def compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, 
             ref_positions = [[object_positions[o][-1]] for o in range(len(bboxes))]
         else:
             ref_positions = [list(object_positions[o]) for o in range(len(bboxes))]
+    kwargs.pop("verbose", None)
     plan = EnergyPlan(bboxes, object_positions, keys, ref_positions=ref_positions,
                       ref_ca_loss_weight=ref_ca_loss_weight, **kwargs)
-    maps = [_cond_map(saved_attn[k]) for k in keys]
     ref_maps = None
     if plan.n_ref:
         ref_maps = []
@@ -129,6 +125,19 @@ def compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, 
             r = per_box[bl][index][k]
             r = r if r.is_cuda else r.cuda()
             ref_maps.append(r[0, :, :, 0].to(torch.float16).contiguous())
+    return plan, ref_maps
+
+
+def compute_ca_lossv3(saved_attn, bboxes, object_positions, guidance_attn_keys, ref_ca_saved_attns=None,
+                      ref_ca_last_token_only=True, ref_ca_word_token_only=False, word_token_indices=None, index=None,
+                      ref_ca_loss_weight=1.0, verbose=False, **kwargs):
+    """Same contract as utils/guidance.py:244-286; returns a 0-d float32 CUDA tensor."""
+    dev = torch.device("cuda")
+    if len(bboxes) == 0:
+        return torch.zeros((), dtype=torch.float32, device=dev)
+    plan, ref_maps = build_plan(bboxes, object_positions, guidance_attn_keys, ref_ca_saved_attns, ref_ca_last_token_only,
+                                ref_ca_word_token_only, word_token_indices, index, ref_ca_loss_weight, **kwargs)
+    maps = [_cond_map(saved_attn[k]) for k in plan.keys]
     loss = torch.zeros((1,), dtype=torch.float32, device=dev)
     ws = torch.empty((MAX_ITEMS + MAX_REF,), dtype=torch.float32, device=dev)
     plan.run(maps, loss, ws, ref_maps=ref_maps)
