@@ -449,6 +449,36 @@ def run_ours(args):
             "algorithmic_bytes": 2.0 * (40960 * 320 * 2 + 320 * 2880),
             "traffic": "see profiles/ (dram__bytes_read+write of the captured launches)"}
 
+    # Reported beside the main number, never inside it: one iteration of latent_backward_guidance --
+    # conditional forward to the last guidance key, energy, d(energy)/d(latents) through the UNet, latent update.  The
+    # reference has no caller for it; this is the cost a caller would pay per iteration.
+    grad_leg = None
+    if rank == 0 and world == 1:
+        try:
+            from theatergen_b200.backward import GuidanceBackward
+            from theatergen_b200.utils.guidance import EnergyPlan
+            net.ip_scale_per_sample = None
+            gb = GuidanceBackward(net)
+            plan_g = EnergyPlan([[(0.1, 0.2, 0.5, 0.8)], [(0.55, 0.3, 0.95, 0.9)]], [[2, 3], [7]],
+                                [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)])
+            lat_g, ctx_g = lat2[:1].to(dev).contiguous(), ctx2[1:2].to(dev).contiguous()
+            n0 = _lib.launch_count()
+            for it in range(3):
+                if it == 1:
+                    torch.cuda.synchronize()
+                    n0 = _lib.launch_count()
+                    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s_.record()
+                loss_g, grad_g = gb.energy_and_grad(lat_g, 801, ctx_g, plan_g, loss_scale=30.0)
+                ops.guidance_update(lat_g.clone(), grad_g, 1.0 / gb.grad_scale, 0.5)
+            e_.record()
+            torch.cuda.synchronize()
+            grad_leg = {"ms_per_iteration": round(s_.elapsed_time(e_) / 2, 3), "launches_per_iteration": (_lib.launch_count() - n0) // 2,
+                        "finite": bool(torch.isfinite(grad_g).all()),
+                        "what": "B=1 conditional forward to up_blocks.1 + energy + input-gradient backward + update, eager"}
+        except Exception as ex:  # the leg is informational; the main line must still print
+            grad_leg = {"error": f"{type(ex).__name__}: {ex}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         total, cores = cpu_denoise_steps(2, 1)
@@ -477,7 +507,7 @@ def run_ours(args):
             "tensor_frac_of_step": round(Kb / (ms_dev * 1e-3) * (K * FLOPS_PER_DENOISE_STEP + FLOPS_PER_DENOISE_STEP
                                                                 + FLOPS_CONTROLNET_STEP) / 1e12 / peaks()[0], 4),
             "roofline": roof, "cpu_baseline": cpu, "graph_replay_ms": graphs,
-            "kernel_breakdown_per_forward": breakdown,
+            "kernel_breakdown_per_forward": breakdown, "guidance_gradient": grad_leg,
         }
         print(json.dumps(out))
     if world > 1:

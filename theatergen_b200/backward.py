@@ -308,3 +308,37 @@ class GuidanceBackward:
                  grad_scale=loss_scale * self.grad_scale)
         grads = tape.backward()
         return loss[0] * loss_scale, grads[sample.data_ptr()]
+
+
+class GuidanceStepGraph:
+    """One `energy_and_grad` evaluation as a CUDA graph (about 1300 kernel launches of a B = 1 forward + backward are
+    launch-bound when enqueued from Python).  The plan's descriptor arrays are baked in by value; latents, timestep and
+    context are static buffers the caller fills before `replay()`."""
+
+    def __init__(self, gb: GuidanceBackward, plan, ctx, loss_scale=1.0, latent_shape=(1, 4, 64, 64)):
+        dev = ctx.device
+        self.gb, self.plan, self.loss_scale = gb, plan, float(loss_scale)
+        self.latents = torch.zeros(latent_shape, dtype=torch.float16, device=dev)
+        self.t = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.ctx = ctx.to(torch.float16).contiguous().clone()
+        self.graph = None
+
+    def capture(self, latents, t):
+        self.latents.copy_(latents)
+        self.t.fill_(float(t))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up: builds the transposed / rotated weight copies outside the capture
+            self.gb.energy_and_grad(self.latents, self.t, self.ctx, self.plan, self.loss_scale)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.grad = self.gb.energy_and_grad(self.latents, self.t, self.ctx, self.plan, self.loss_scale)
+        return self
+
+    def replay(self, latents, t):
+        self.latents.copy_(latents)
+        self.t.fill_(float(t))
+        self.graph.replay()
+        return self.loss, self.grad

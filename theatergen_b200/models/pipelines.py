@@ -70,7 +70,7 @@ def latent_backward_guidance(adapter, scheduler, unet, cond_embeddings, index, b
     recorded forward (theatergen_b200/backward.py -- the reference uses autograd, :102), then
     `latents -= grad * sqrt(1 - alpha_prod_t)` (:106-115, the DDIM branch: the scheduler has no `sigmas`).
     Returns (latents, loss) like the reference; `loss` is a 0-d float32 CUDA tensor (energy * loss_scale)."""
-    from ..backward import GuidanceBackward
+    from ..backward import GuidanceBackward, GuidanceStepGraph
     iteration = 0
     if index < max_index_step:
         if isinstance(max_iter, list):
@@ -86,10 +86,23 @@ def latent_backward_guidance(adapter, scheduler, unet, cond_embeddings, index, b
         while loss.item() / loss_scale > loss_threshold and iteration < max_iter and index < max_index_step:
             if len(bboxes) == 0:
                 break
-            plan, ref_maps = guidance.build_plan(bboxes, object_positions, keys, ref_ca_saved_attns=ref_ca_saved_attns,
-                                                 index=index, **kwargs)
-            loss, grad = gb.energy_and_grad(scheduler.scale_model_input(latents, t), t, cond_embeddings, plan,
-                                            loss_scale=loss_scale, ref_maps=ref_maps)
+            if ref_ca_saved_attns is None and getattr(unet, "guidance_graphs", True):
+                # forward + energy + backward replayed as one CUDA graph per (layout, prompt) -- built on first use
+                gkey = repr((bboxes, object_positions, keys, sorted(kwargs.items()), loss_scale, cond_embeddings.data_ptr(),
+                             tuple(latents.shape)))
+                graphs = unet.__dict__.setdefault("_guidance_graphs", {})
+                sg = graphs.get(gkey)
+                if sg is None:
+                    plan, _ = guidance.build_plan(bboxes, object_positions, keys, index=index, **kwargs)
+                    sg = graphs[gkey] = GuidanceStepGraph(gb, plan, cond_embeddings, loss_scale, tuple(latents.shape))
+                    sg.capture(scheduler.scale_model_input(latents, t), t)
+                sg.ctx.copy_(cond_embeddings)
+                loss, grad = sg.replay(scheduler.scale_model_input(latents, t), t)
+            else:
+                plan, ref_maps = guidance.build_plan(bboxes, object_positions, keys, ref_ca_saved_attns=ref_ca_saved_attns,
+                                                     index=index, **kwargs)
+                loss, grad = gb.energy_and_grad(scheduler.scale_model_input(latents, t), t, cond_embeddings, plan,
+                                                loss_scale=loss_scale, ref_maps=ref_maps)
             if torch.isnan(loss):
                 print("**Loss is NaN**")
             if not owned:  # the reference rebinds `latents` (out of place); the caller's tensor stays untouched
