@@ -3,9 +3,10 @@ return tuples (generate_semantic_guidance :175-490, final_image_generation :592-
 latent_backward_guidance :62-128, encode/decode :130-173), with the per-timestep hot loops executed by
 theatergen_b200.engine.DenoiseEngine (CUDA-graph replayed libtheatergen.so kernels).
 
-What is NOT re-implemented here and is reached through the objects the caller passes in, exactly like the reference
-does (duck-typed): `adapter.pipe.encode_prompt` (CLIP text), `adapter.pipe.vae` / `image_processor` (VAE),
-`adapter.get_image_embeds(pil_image=...)` (CLIP vision), `processor` (the line-art detector).  `controlnetpipe.controlnet` is a
+Reached through the objects the caller passes in, exactly like the reference does (duck-typed):
+`adapter.pipe.encode_prompt` (its `text_encoder` can be theatergen_b200.clip_text.TGCLIPText), `adapter.pipe.vae` /
+`image_processor` (theatergen_b200.vae.TGAutoencoderKL), `adapter.get_image_embeds(pil_image=...)`
+(theatergen_b200.clip_vision.TGCLIPVision), `processor` (the line-art detector: not re-implemented).  `controlnetpipe.controlnet` is a
 theatergen_b200.controlnet.TGControlNet on the kernel path (any other module is called eagerly per step).  `basever == 'xl'` raises: SDXL is outside the metric.
 
 Reference quirks kept on purpose: the stage-1 prompt is re-encoded from `ip_prompt` and the
