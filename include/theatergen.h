@@ -187,6 +187,14 @@ int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const 
                        float fg_weight, float bg_weight, float grad_scale, float ref_eps, float* loss_out,
                        float* workspace, void* stream);
 
+/* Tile selection of tg_gemm / tg_conv3x3.  A measured table (tools/gemm_autotune.py -> theatergen_b200/gemm_tuned.json,
+ * loaded when the library is opened) overrides the built-in cost model per problem shape: tile width bn in
+ * {64,128,160,192,256}, split-K factor 1..8, CTA pairing 0/1; conv != 0 for the implicit-GEMM convolution (K = 9 Cin).
+ * tg_gemm_force_tile(bn,...) forces one configuration for every following call (bn = 0: off) -- tuner / tests only. */
+int tg_gemm_set_tuned(int M, int N, int K, int act, int conv, int bn, int split, int pair);
+int tg_gemm_clear_tuned(void);
+int tg_gemm_force_tile(int bn, int split, int pair);
+
 /* ---- input gradients of the guidance step: `torch.autograd.grad(loss, [latents])` of latent_backward_guidance
  * (models/pipelines.py:62-128, :102).  The weights are frozen, so GEMM / convolution backward is tg_gemm / tg_conv3x3 on
  * transposed / rotated weight copies; these entry points are the remaining operator backwards.  fp16 tensors, fp32 math. */

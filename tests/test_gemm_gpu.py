@@ -104,3 +104,37 @@ def test_conv3x3(B, H, W, Cin, Cout):
     ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(),
                                      padding=1) + temb.float()[:, :, None, None]
     _close(out, ref.permute(0, 2, 3, 1), 3e-3, 3e-3)
+
+
+def test_forced_and_tuned_tiles_agree_with_the_model_choice():
+    """tg_gemm_force_tile / tg_gemm_set_tuned (tools/gemm_autotune.py): every valid configuration computes the same GEMM;
+    invalid ones are refused; the table is consulted per shape and cleared again."""
+    from theatergen_b200 import _lib, ops
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 1000, 640, 1280
+    a = torch.randn(M, K, generator=g).half().cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).half().cuda()
+    b = torch.randn(N, generator=g).half().cuda()
+    ref = a.float() @ w.float().t() + b.float()
+    base = ops.gemm(a, w, b)
+    try:
+        for bn, split, pair in [(64, 1, 0), (128, 1, 1), (160, 2, 0), (128, 4, 1), (64, 8, 0)]:
+            assert L.tg_gemm_force_tile(bn, split, pair) == 0
+            out = ops.gemm(a, w, b)
+            assert (out.float() - ref).abs().max().item() < 2e-2, (bn, split, pair)
+            assert (out.float() - base.float()).abs().max().item() < 8e-3
+        L.tg_gemm_force_tile(256, 1, 0)  # 640 % 256 != 0
+        with pytest.raises(RuntimeError):
+            ops.gemm(a, w, b)
+    finally:
+        L.tg_gemm_force_tile(0, 1, 0)
+    assert L.tg_gemm_set_tuned(M, N, K, 0, 0, 192, 1, 0) != 0      # invalid entry refused
+    assert L.tg_gemm_set_tuned(M, N, K, 0, 0, 64, 2, 1) == 0
+    tuned = ops.gemm(a, w, b)
+    L.tg_gemm_force_tile(64, 2, 1)
+    forced = ops.gemm(a, w, b)
+    L.tg_gemm_force_tile(0, 1, 0)
+    assert torch.equal(tuned, forced)                                # the table entry selected exactly that tile
+    assert L.tg_gemm_clear_tuned() == 0
+    assert torch.equal(ops.gemm(a, w, b), base)

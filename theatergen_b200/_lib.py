@@ -32,6 +32,9 @@ _SIGS = {
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
     "tg_im2col_patch": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_embed_tokens": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_gemm_set_tuned": (ci, [ci, ci, ci, ci, ci, ci, ci, ci]),
+    "tg_gemm_clear_tuned": (ci, []),
+    "tg_gemm_force_tile": (ci, [ci, ci, ci]),
     "tg_layernorm_bwd": (ci, [vp, ci, vp, vp, ci, vp, ci, ci, ci, cf, vp]),
     "tg_groupnorm_bwd": (ci, [vp, vp, vp, vp, vp, ci, ci, ci, cf, ci, vp]),
     "tg_softmax_bwd_rows": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, cf, vp]),
@@ -74,7 +77,23 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = l
+        _load_tuned(l)
     return _lib
+
+
+TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuned.json")
+
+
+def _load_tuned(l):
+    """Measured GEMM tile choices per problem shape (tools/gemm_autotune.py); TG_GEMM_TUNED=0 keeps the cost model only."""
+    if os.environ.get("TG_GEMM_TUNED", "1") == "0" or not os.path.exists(TUNED_PATH):
+        return 0
+    import json
+    n = 0
+    for M, N, K, act, conv, bn, split, pair in json.load(open(TUNED_PATH))["entries"]:
+        if l.tg_gemm_set_tuned(M, N, K, act, conv, bn, split, pair) == 0:
+            n += 1
+    return n
 
 
 def exported_symbols():

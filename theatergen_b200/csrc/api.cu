@@ -90,6 +90,11 @@ int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int 
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
 }
+int tg_gemm_set_tuned(int M, int N, int K, int act, int conv, int bn, int split, int pair) {
+  return tg::gemm_set_tuned(M, N, K, act, conv, bn, split, pair);
+}
+int tg_gemm_clear_tuned(void) { return tg::gemm_clear_tuned(); }
+int tg_gemm_force_tile(int bn, int split, int pair) { return tg::gemm_force_tile(bn, split, pair); }
 int tg_layernorm_bwd(const tg_half* x, int ldx, const tg_half* gamma, const tg_half* dy, int lddy, tg_half* dx, int lddx,
                      int M, int C, float eps, void* stream) {
   TG_CHECK(x && gamma && dy && dx, "tg_layernorm_bwd: null pointer");

@@ -30,6 +30,8 @@
 // ip_adapter/attention.py:269-367, ip_adapter/transformer_2d.py:288-342, diffusers ResnetBlock2D).
 #include <stdlib.h>
 
+#include <unordered_map>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -673,8 +675,56 @@ static bool pair_enabled() {
 //     such groups do not overlap; a stage also cannot beat ~74 B/clk of per-SM TMA bandwidth;
 //   whichever is larger.  Wider tiles are cheaper per flop, pairs halve the weight bytes per SM, wave quantisation decides
 //   the rest; split-K fills the SMs when M is small and K long.
-static void pick_tile(int M, int N, int K, int act, int num_sms, int* bn_out, int* split_out, int* pair_out) {
+// Measured choices take precedence over the model: tools/gemm_autotune.py times every valid (tile width, split, pairing)
+// per problem shape on the GPU (cold weights, warm activations) and theatergen_b200/gemm_tuned.json is loaded into this
+// table when the library is opened.  Shapes without an entry fall through to the cost model below.
+struct TileCfg {
+  int bn, split, pair;
+};
+static std::unordered_map<unsigned long long, TileCfg> g_tuned;
+static TileCfg g_forced = {0, 1, 0};  // bn == 0: no override (tuner only)
+static unsigned long long tile_key(int M, int N, int K, int act, int conv) {
+  return (unsigned long long)M | ((unsigned long long)N << 24) | ((unsigned long long)K << 40) |
+         ((unsigned long long)(act == 2) << 56) | ((unsigned long long)(conv != 0) << 57);
+}
+static bool tile_cfg_valid(int M, int N, int K, int act, int bn, int split, int pair) {
+  if (bn != 256 && bn != 192 && bn != 160 && bn != 128 && bn != 64) return false;
+  if (N % bn || (act == 2 && (bn % 128 || split != 1))) return false;
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
+  if (pair != 0 && pair != 1) return false;
+  if (pair && num_m < 2) return false;
+  if (split < 1 || split > MAX_SPLIT || split > nk) return false;
+  if (split > 1 && ((size_t)num_m * (N / bn) * split * BM * bn * 4 > SPLITK_WS_BYTES || num_m * (N / bn) > SPLITK_MAX_TILES))
+    return false;
+  return true;
+}
+int gemm_set_tuned(int M, int N, int K, int act, int conv, int bn, int split, int pair) {
+  TG_CHECK(M > 0 && M < (1 << 24) && N > 0 && N < (1 << 16) && K > 0 && K < (1 << 16), "gemm_set_tuned: shape out of range");
+  TG_CHECK(tile_cfg_valid(M, N, K, act, bn, split, pair), "gemm_set_tuned: invalid tile %d/%d/%d for M=%d N=%d K=%d act=%d",
+           bn, split, pair, M, N, K, act);
+  g_tuned[tile_key(M, N, K, act, conv)] = TileCfg{bn, split, pair};
+  return 0;
+}
+int gemm_clear_tuned() {
+  g_tuned.clear();
+  return 0;
+}
+int gemm_force_tile(int bn, int split, int pair) {  // bn = 0 switches the override off
+  g_forced = TileCfg{bn, split, pair};
+  return 0;
+}
+
+static void pick_tile(int M, int N, int K, int act, int conv, int num_sms, int* bn_out, int* split_out, int* pair_out) {
+  const int num_m = (M + BM - 1) / BM, nk = K / BK;
+  if (!g_tuned.empty()) {
+    auto it = g_tuned.find(tile_key(M, N, K, act, conv));
+    if (it != g_tuned.end()) {
+      *bn_out = it->second.bn;
+      *split_out = it->second.split;
+      *pair_out = it->second.pair;
+      return;
+    }
+  }
   const int cands[5] = {256, 192, 160, 128, 64};
   double best_cost = 1e30;
   *bn_out = 64;
@@ -724,7 +774,14 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   if (get_scratch(&sc)) return -1;
   const int n_out = g.act == 2 ? g.N / 2 : g.N;
   int bn, splits, pair;
-  pick_tile(g.M, g.N, g.K, g.act, sc->num_sms, &bn, &splits, &pair);
+  if (g_forced.bn) {
+    TG_CHECK(tile_cfg_valid(g.M, g.N, g.K, g.act, g_forced.bn, g_forced.split, g_forced.pair),
+             "forced tile %d/%d/%d is not valid for M=%d N=%d K=%d act=%d", g_forced.bn, g_forced.split, g_forced.pair, g.M,
+             g.N, g.K, g.act);
+    bn = g_forced.bn, splits = g_forced.split, pair = g_forced.pair;
+  } else {
+    pick_tile(g.M, g.N, g.K, g.act, g.mode, sc->num_sms, &bn, &splits, &pair);
+  }
   CUtensorMap c;  // epilogue chunks: 32 rows x 32 columns (64-byte rows, 64B swizzle)
   if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) return -1;
   g.num_m = (g.M + BM - 1) / BM;

@@ -110,7 +110,7 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, ou
                 lambda: _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
                                0 if rowbias is None else rowbias.stride(0), _p(res2),
                                0 if res2 is None else res2.stride(0), act, float(out_scale), _p(out), Cout, _stream()),
-                tag=f"conv M={Mc} N={Cout} K={9 * Cin}")
+                tag=f"conv M={Mc} N={Cout} K={9 * Cin} B={B} H={H} W={W}")
     _lib.check(rc, "tg_conv3x3")
     return out
 

@@ -24,6 +24,10 @@ def main():
             cases.append((f"lin {name}", M, N, K, lambda a=a, w=w, bias=bias: ops.gemm(a, w, bias, act=ops.TG_ACT_GEGLU)))
         else:
             cases.append((f"lin {name}", M, N, K, lambda a=a, w=w: ops.gemm(a, w)))
+    for name, M, N, K in (("C->C 320 +res", 40960, 320, 320), ("C->C 640 +res", 10240, 640, 640),
+                          ("C->C 1280 +res", 2560, 1280, 1280), ("ff2 320 +res", 40960, 320, 1280)):
+        a, w, bias, res = r(M, K), r(N, K), r(N), r(M, N)
+        cases.append((f"lin {name}", M, N, K, lambda a=a, w=w, bias=bias, res=res: ops.gemm(a, w, bias, residual=res)))
     for H, cin, cout in ((64, 320, 320), (32, 1280, 640), (16, 1280, 1280)):
         x, w = r(B, H, H, cin), r(cout, 3, 3, cin)
         cases.append((f"conv {H}x{H} {cin}->{cout}", B * H * H, cout, 9 * cin, lambda x=x, w=w: ops.conv3x3(x, w)))
