@@ -138,3 +138,36 @@ def test_forced_and_tuned_tiles_agree_with_the_model_choice():
     assert torch.equal(tuned, forced)                                # the table entry selected exactly that tile
     assert L.tg_gemm_clear_tuned() == 0
     assert torch.equal(ops.gemm(a, w, b), base)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 640), (3, 32, 32, 640, 1280), (1, 16, 16, 1280, 640),
+                                            (1, 64, 64, 128, 128)])
+def test_conv3x3_patch_reuse_tiles(B, H, W, Cin, Cout):
+    """The KY3 stages of the convolution (one (box_h + 2)-row input patch serves the three ky taps; pair tiles of 64 / 128 /
+    160 columns, image rows <= 64 pixels) against torch, with and without split-K, beside the tap-per-k-block ring that
+    256-column tiles and single-CTA tiles keep.  Borders exercise the TMA zero fill above / below / beside the image."""
+    from theatergen_b200 import _lib, ops
+    L = _lib.lib()
+    x = _rand((B, H, W, Cin), 1)
+    w = _rand((Cout, 3, 3, Cin), 2, (9 * Cin) ** -0.5)
+    bias = _rand((Cout,), 3)
+    res = _rand((B, H, W, Cout), 5)
+    ref = (torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias.float(),
+                                      padding=1).permute(0, 2, 3, 1) + res.float())
+    outs = {}
+    try:
+        for bn, split, pair in [(64, 1, 1), (128, 1, 1), (160, 1, 1), (128, 3, 1), (64, 2, 1), (256, 1, 1), (128, 1, 0)]:
+            if Cout % bn:
+                continue
+            assert L.tg_gemm_force_tile(bn, split, pair) == 0
+            outs[(bn, split, pair)] = ops.conv3x3(x, w, bias, residual=res)
+    finally:
+        L.tg_gemm_force_tile(0, 1, 0)
+    for k, o in outs.items():
+        _close(o, ref, 4e-3, 4e-3)
+    # same tile, same k order per accumulator -> the patch path is bit-identical to itself across launches
+    L.tg_gemm_force_tile(128, 1, 1)
+    try:
+        assert torch.equal(ops.conv3x3(x, w, bias, residual=res), outs[(128, 1, 1)])
+    finally:
+        L.tg_gemm_force_tile(0, 1, 0)

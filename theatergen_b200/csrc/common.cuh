@@ -302,6 +302,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 // row-major fp16 [rows, K] seen as [K/64 chunks][rows][64]; box = [kc chunks][box_rows][64], SWIZZLE_128B: ONE instruction
 // lands kc consecutive K-major [box_rows x 64] tiles (chunks past K/64 are zero-filled)
 int make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows, uint32_t kc);
+int make_tmap_w_ky3(CUtensorMap* out, const void* base, uint64_t rows, uint64_t Cin, uint32_t box_rows);
 // 4D NHWC fp16 [B, H, W, C]; box = [bb, bh, bw, 64], SWIZZLE_128B, OOB zero fill (conv padding)
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
                    uint32_t bh, uint32_t bw);

@@ -59,16 +59,26 @@ struct GemmArgs {
   int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64), 3 gelu(erf)
   float out_scale;
   int num_m, num_n, splits;
+  int patch_bytes, ky_stride;  // KY3 convolution: bytes of the (box_h + 2)-row input patch, bytes of one image row in it
   float* ws;   // split-K partials: [tile][split][BN/4][128][4] fp32
   int* sem;    // split-K arrival counters, one per tile (self-resetting)
   long long* prof;  // measurement only (tg_gemm_set_prof): per CTA {total, producer wait, MMA wait full, MMA wait acc, epilogue wait} cycles
 };
 
-template <int BN, int STAGES, bool PAIR>
+// KY3 (3x3 convolution, image rows no wider than 64 pixels, one image per tile): a stage holds ONE input patch of
+// box_h + 2 image rows (<= 32 KB) and the weight chunks of the three taps (ky = 0,1,2) of one (kx, channel block).  The
+// three taps read the same patch at offsets of one image row (W x 128 B, a multiple of the 1024-byte swizzle period), so
+// the activation bytes an SM ingests per three k-blocks drop from 48 KB to 16 KB + 256 B x W.
+static constexpr int KY3_PATCH_MAX = 32768;
+// Wider tiles would fit only two such stages (80 / 68 KB): measured slower than the tap-per-k-block ring with cold weights
+// (16x16 level, N = 1280: 83 vs 76 us), so tiles of 192 / 256 columns keep the three-stage ring of two-k-block stages.
+static constexpr int KY3_MAX_BN = 160;
+template <int BN, int STAGES, bool PAIR, bool KY3 = false>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;                    // one k-block of A
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // one k-block of B; a CTA of a pair stages half of the weight tile
-  static constexpr int STAGE_BYTES = KPS * (A_BYTES + B_BYTES);  // [A kb0 | A kb1 | B kb0 | B kb1]
+  static constexpr int A_STAGE_BYTES = KY3 ? KY3_PATCH_MAX : KPS * A_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + (KY3 ? 3 : KPS) * B_BYTES;  // [A kb0 | A kb1 | B kb0 | B kb1]
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_WARPS * EPI_BUF_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 32 + 1024;  // + alignment slack
@@ -224,11 +234,12 @@ __device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[4]
   }
 }
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool KY3 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
-  using L = GemmSmem<BN, STAGES, PAIR>;
+  using L = GemmSmem<BN, STAGES, PAIR, KY3>;
+  static_assert(!KY3 || PAIR, "the KY3 convolution path exists for CTA pairs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -240,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nk = g.K / BK;
+  const int nk = KY3 ? g.K / (3 * BK) : g.K / BK;  // KY3: units of (kx, channel block) = three k-blocks each
   const int S = g.splits;
   // PAIR: a cluster of two CTAs owns the M-tile pair (2*pm, 2*pm + 1); rank selects the CTA's 128 rows and the half
   // of the weight tile it stages.  Rank 0 is the leader (MMA issuer; owner of the full / accumulator-empty barriers).
@@ -304,6 +315,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         // One stage = KPS consecutive k-blocks: the loads of a stage are issued back to back after ONE wait.  Measured on
         // B200 (tools/probes): a group of TMA loads issued after a barrier wait costs ~570 cycles + ~70 per extra load,
         // whatever its size, and groups do not overlap each other -- so a stage must carry as much MMA work as possible.
+        if constexpr (KY3) {
+          // one patch (A) + one 4D weight box (the chunks of ky = 0,1,2) per stage: two TMA instructions for three k-blocks
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            if (g.prof) {
+              const long long t0 = clock64();
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              p_wait += clock64() - t0;
+            } else {
+              mbar_wait(&empty_bar[s], ph ^ 1);
+            }
+            uint8_t* sa = smem + s * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_STAGE_BYTES;
+            const uint32_t bytes = (uint32_t)g.patch_bytes + 3 * L::B_BYTES;
+            const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
+            const int kx = kb / cblk, cb = kb - kx * cblk;
+            tma_load_4d_2sm(sa, &tmA2, fb, cb * BK, kx - 1, conv_y0 - 1, conv_b0);
+            tma_load_4d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb, 0);
+          }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -366,6 +400,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         }
         tc_fence_after();
         const uint32_t d_addr = tmem_base + as * ACC_STRIDE;
+        if constexpr (KY3) {
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            if (g.prof) {
+              const long long t0 = clock64();
+              mbar_wait(&full_bar[s], ph);
+              m_wait_full += clock64() - t0;
+            } else {
+              mbar_wait(&full_bar[s], ph);
+            }
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+            const uint32_t b_base = a_base + L::A_STAGE_BYTES;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint32_t a_addr = a_base + ky * g.ky_stride, b_addr = b_base + ky * L::B_BYTES;
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
+                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
+                umma_f16_ss_2sm(d_addr, da, db, idesc, (kb > kb0 || ky > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            tc_commit_2sm(&empty_bar[s], 0x3);
+          }
+          tc_commit_2sm(&acc_full[as], 0x3);
+          continue;
+        }
         for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -636,18 +699,22 @@ int gemm_init() {
   return get_scratch(&s);
 }
 
-template <int BN, int STAGES, bool PAIR>
+template <int BN, int STAGES, bool PAIR, bool KY3 = false>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
                        GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
-  using L = GemmSmem<BN, STAGES, PAIR>;
+  using L = GemmSmem<BN, STAGES, PAIR, KY3>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<BN, STAGES, PAIR>;
+  auto kern = gemm_tc_kernel<BN, STAGES, PAIR, KY3>;
   if (!attr_set) {
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   CUtensorMap b;
-  if (make_tmap_kchunks(&b, Wt, g.N, g.K, PAIR ? BN / 2 : BN, KPS)) return -1;
+  if (KY3) {
+    if (make_tmap_w_ky3(&b, Wt, g.N, g.Cin, BN / 2)) return -1;
+  } else {
+    if (make_tmap_kchunks(&b, Wt, g.N, g.K, PAIR ? BN / 2 : BN, KPS)) return -1;
+  }
   const int rows_m = PAIR ? (g.num_m + 1) / 2 : g.num_m;
   const int work = rows_m * g.num_n * g.splits;
   const int max_workers = PAIR ? sc.num_sms / 2 : sc.num_sms;
@@ -659,6 +726,14 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __hal
 
 // CTA pairs (cta_group::2) are the default whenever a problem has >= 2 M-tiles; TG_GEMM_PAIR=0 forces single-CTA tiles
 // (A/B measurements).
+static bool conv_ky3_enabled() {  // TG_CONV_KY3=0: every convolution on the tap-per-k-block path (A/B measurements)
+  static int use = -1;
+  if (use < 0) {
+    const char* e = getenv("TG_CONV_KY3");
+    use = (e && e[0] == '0') ? 0 : 1;
+  }
+  return use == 1;
+}
 static bool pair_enabled() {
   static int use = -1;
   if (use < 0) {
@@ -714,7 +789,8 @@ int gemm_force_tile(int bn, int split, int pair) {  // bn = 0 switches the overr
   return 0;
 }
 
-static void pick_tile(int M, int N, int K, int act, int conv, int num_sms, int* bn_out, int* split_out, int* pair_out) {
+static void pick_tile(int M, int N, int K, int act, int conv, int patch_bytes, int num_sms, int* bn_out, int* split_out,
+                      int* pair_out) {
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
   if (!g_tuned.empty()) {
     auto it = g_tuned.find(tile_key(M, N, K, act, conv));
@@ -749,14 +825,17 @@ static void pick_tile(int M, int N, int K, int act, int conv, int num_sms, int* 
         while (s > 1 && ((size_t)num_m * (N / bn) * s * BM * bn * 4 > SPLITK_WS_BYTES || num_m * (N / bn) > SPLITK_MAX_TILES)) --s;
       }
       const int waves = (tiles * s + workers - 1) / workers;
-      const double mma = KPS * 4.0 * (bn / 2.0 > 88.0 ? bn / 2.0 : 88.0);
-      const double stage_bytes = KPS * (16384.0 + (pair ? 64.0 : 128.0) * bn);
-      double tma = 570.0 + 70.0 * KPS;  // KPS A loads + 1 weight load
+      // KY3 convolution stages (pairs only): three k-blocks share one input patch -> one A load of patch_bytes
+      const bool ky3 = pair && patch_bytes > 0 && bn <= KY3_MAX_BN;
+      const int kps = ky3 ? 3 : KPS;
+      const double mma = kps * 4.0 * (bn / 2.0 > 88.0 ? bn / 2.0 : 88.0);
+      const double stage_bytes = ky3 ? patch_bytes + 3 * 64.0 * bn : KPS * (16384.0 + (pair ? 64.0 : 128.0) * bn);
+      double tma = 570.0 + 70.0 * (ky3 ? 1 : KPS);  // A loads + 1 weight load
       if (stage_bytes / 74.0 > tma) tma = stage_bytes / 74.0;
       const double per_stage = mma > tma ? mma : tma;
       const int kb_per_item = (nk + s - 1) / s;
       const double epi = 1500.0 + 8.0 * bn + (s > 1 ? 6.0 * bn * s : 0.0);
-      const double cost = waves * (per_stage * ((kb_per_item + KPS - 1) / KPS) + epi);
+      const double cost = waves * (per_stage * ((kb_per_item + kps - 1) / kps) + epi);
       if (cost < best_cost * 0.999) {
         best_cost = cost;
         *bn_out = bn;
@@ -780,8 +859,10 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
              g.N, g.K, g.act);
     bn = g_forced.bn, splits = g_forced.split, pair = g_forced.pair;
   } else {
-    pick_tile(g.M, g.N, g.K, g.act, g.mode, sc->num_sms, &bn, &splits, &pair);
+    pick_tile(g.M, g.N, g.K, g.act, g.mode, g.patch_bytes, sc->num_sms, &bn, &splits, &pair);
   }
+  // KY3 stages for pair-tiled convolutions whose tile lies inside one image (conv3x3_nhwc prepared the patch map as a2)
+  const bool ky3 = pair && g.patch_bytes > 0 && bn <= KY3_MAX_BN && splits <= g.K / (3 * BK);
   CUtensorMap c;  // epilogue chunks: 32 rows x 32 columns (64-byte rows, 64B swizzle)
   if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) return -1;
   g.num_m = (g.M + BM - 1) / BM;
@@ -791,6 +872,13 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   g.sem = sc->sem;
   g.prof = g_prof;
   // stages of KPS k-blocks; a CTA of a pair stages half of the weight tile -> deeper rings in the same shared memory
+  if (ky3) {  // stage = patch (<= 32 KB) + 3 weight half-chunks
+    switch (bn) {
+      case 160: return launch_gemm<160, 3, true, true>(a1, a2, Wt, c, g, *sc, st);   // 62 KB
+      case 128: return launch_gemm<128, 3, true, true>(a1, a2, Wt, c, g, *sc, st);   // 56 KB
+      default: return launch_gemm<64, 4, true, true>(a1, a2, Wt, c, g, *sc, st);     // 44 KB
+    }
+  }
   if (pair) {
     switch (bn) {
       case 256: return launch_gemm<256, 3, true>(a1, a2, Wt, c, g, *sc, st);   // 64 KB stages
@@ -854,9 +942,17 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
   g.M = B * H * W; g.N = Cout; g.K = 9 * Cin; g.K1 = g.K; g.mode = 1;
   g.H = H; g.W = W; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
   fill_args(g, e);
-  CUtensorMap a1;
+  CUtensorMap a1, a2;
   if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, box_w)) return -1;
-  return dispatch(a1, a1, g, Wt, out, ldc, st);
+  a2 = a1;
+  // KY3: the tile is box_h whole image rows of one image -> the three ky taps of a (kx, channel block) read one patch of
+  // box_h + 2 rows (TMA zero-fills the rows / columns outside the image)
+  if (conv_ky3_enabled() && box_b == 1 && box_w == W && W % 8 == 0 && (box_h + 2) * W * 128 <= KY3_PATCH_MAX) {
+    if (make_tmap_nhwc(&a2, X, B, H, W, Cin, 1, box_h + 2, W)) return -1;
+    g.patch_bytes = (box_h + 2) * W * 128;
+    g.ky_stride = W * 128;
+  }
+  return dispatch(a1, a2, g, Wt, out, ldc, st);
 }
 
 }  // namespace tg

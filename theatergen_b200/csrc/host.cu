@@ -82,6 +82,25 @@ int make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return 0;
 }
 
+// Weights of a 3x3 convolution [N][ky][kx][Cin] seen as [ky][kx*Cin/64 + cb][N][64]: one box {64, box_rows, 1, 3} brings
+// the 64-channel chunks of the three taps ky = 0,1,2 of one (kx, channel block) -- the KY3 stage of gemm_tc_kernel.
+int make_tmap_w_ky3(CUtensorMap* out, const void* base, uint64_t rows, uint64_t Cin, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && Cin % 64 == 0, "tmap w_ky3: alignment (base=%p Cin=%llu)", base,
+           (unsigned long long)Cin);
+  cuuint64_t dims[4] = {64, rows, 3 * Cin / 64, 3};
+  cuuint64_t strides[3] = {9 * Cin * 2, 128, 3 * Cin * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 3};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(w_ky3 rows=%llu Cin=%llu box_rows=%u) -> %d", (unsigned long long)rows,
+           (unsigned long long)Cin, box_rows, (int)r);
+  return 0;
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
                    uint32_t bh, uint32_t bw) {
   EncodeTiledFn enc = get_encode();

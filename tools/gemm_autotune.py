@@ -90,6 +90,8 @@ def main():
     ap.add_argument("--reps", type=int, default=7)
     ap.add_argument("--min-gain", type=float, default=0.04, help="keep a measured choice only if it beats the model by this much")
     ap.add_argument("--report", default=None)
+    ap.add_argument("--only", default=None, choices=["lin", "conv"], help="restrict the search to one kind of shape")
+    ap.add_argument("--min-calls", type=float, default=0.0, help="skip shapes with fewer calls per bench step")
     ap.add_argument("--out", default=_lib.TUNED_PATH)
     args = ap.parse_args()
     dev = torch.device("cuda")
@@ -117,6 +119,8 @@ def main():
     saved = total_default = 0.0
     for key, calls in sorted(shapes.items(), key=lambda kv: -kv[1]):
         kind, M, N, K, act2, B, H, W = key
+        if (args.only and kind != args.only) or calls < args.min_calls:
+            continue
         wt = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).half()
         bias = (torch.randn(N, device=dev, generator=g) * 0.1).half()
         if kind == "conv":
