@@ -13,6 +13,8 @@ per = defaultdict(dict)
 with open(path, newline="") as f:
     lines = [l for l in f if not l.startswith("==")]
 for r in csv.DictReader(lines):
+    if "gemm_tc_kernel" not in r["Kernel Name"]:  # the launch list may hold every kernel of the timed region
+        continue
     v = float(r["Metric Value"].replace(",", "")) * unit_scale.get(r.get("Metric Unit", ""), 1)
     per[r["ID"]][r["Metric Name"]] = v
     per[r["ID"]]["name"] = r["Kernel Name"].split("(")[0].replace("void ", "")
