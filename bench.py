@@ -443,7 +443,7 @@ def run_ours(args):
         burst = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) \
             if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
         roof["representative_launch"] = {
-            "what": "conv3x3 320->320 @64x64, B=10 (gemm_tc_kernel<160,3,pair>, CONV3 mode), timed alone, 20 launches",
+            "what": "conv3x3 320->320 @64x64, B=10 (gemm_tc_kernel<160,3,pair,KY3>: patch-reuse conv stages), timed alone, 20 launches",
             "us": round(us, 2), "achieved": round(fl / us / 1e6, 1), "peak": burst, "unit": "TFLOP/s",
             "frac": round(fl / us / 1e6 / burst, 4), "algorithmic_flops": fl,
             "algorithmic_bytes": 2.0 * (40960 * 320 * 2 + 320 * 2880),
