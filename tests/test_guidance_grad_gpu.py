@@ -152,3 +152,38 @@ def test_graph_replay_equals_eager_and_timing():
     t_torch = ms(lambda: _oracle_grad(OU, sd, x, ctx, 801, 0.4, KEYS, 30.0, torch.float16, sdd=sd16), n=3)
     print(f"guidance gradient, one evaluation: graph {t_graph:.2f} ms, eager {t_eager:.2f} ms, torch fp16 autograd of the "
           f"oracle on the same GPU {t_torch:.1f} ms (whole UNet forward, weights resident)")
+
+
+def test_guidance_graph_cache_is_bounded_and_tracks_the_ip_scale():
+    from theatergen_b200.models import pipelines
+    from theatergen_b200.scheduler import DDIMScheduler
+    from theatergen_b200.unet import TGUNet
+    OU, sd, x, ctx = _setup(3)
+    net = TGUNet(sd)
+    sch = DDIMScheduler()
+    sch.set_timesteps(50)
+    t = int(sch.timesteps[1])
+    big = torch.tensor(1e4, device="cuda")
+
+    def run(bboxes, scale):
+        for p in net.attn_processors.values():
+            if hasattr(p, "scale"):
+                p.scale = scale
+        return pipelines.latent_backward_guidance(None, sch, net, ctx.cuda(), 1, bboxes, POSITIONS, t, x.cuda(), big,
+                                                  loss_scale=30, loss_threshold=0.0, max_iter=1, guidance_attn_keys=KEYS[:2])
+    old = pipelines.MAX_GUIDANCE_GRAPHS
+    pipelines.MAX_GUIDANCE_GRAPHS = 2
+    try:
+        a, _ = run(BBOXES, 0.4)
+        assert len(net._guidance_graphs) == 1
+        b, _ = run(BBOXES, 0.4)                       # same layout: replay, bit-identical
+        assert len(net._guidance_graphs) == 1 and torch.equal(a, b)
+        c, _ = run(BBOXES, 0.0)                       # another IP scale is another graph (the scale is baked in)
+        assert len(net._guidance_graphs) == 2 and not torch.equal(a, c)
+        run([[(0.0, 0.0, 0.5, 0.5)], [(0.5, 0.5, 1.0, 1.0)]], 0.4)
+        assert len(net._guidance_graphs) == 2         # the oldest graph was evicted
+        net.guidance_graphs = False
+        e, _ = run(BBOXES, 0.4)                       # eager evaluation gives the graph's result
+        assert torch.equal(a, e)
+    finally:
+        pipelines.MAX_GUIDANCE_GRAPHS = old

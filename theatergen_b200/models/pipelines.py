@@ -28,6 +28,7 @@ from ..unet import TGUNet
 from ..utils import guidance, schedule
 
 torch_device = "cuda"
+MAX_GUIDANCE_GRAPHS = 4  # captured guidance-gradient graphs kept per UNet (least recently used is dropped)
 DEFAULT_GUIDANCE_ATTN_KEYS = [("mid", 0, 0, 0), ("up", 1, 0, 0), ("up", 1, 1, 0), ("up", 1, 2, 0)]  # pipelines.py:21
 NEGATIVE_SO = "background, multiple objects, incomplete, lowres, bad anatomy, low quality, obscured"
 
@@ -89,14 +90,18 @@ def latent_backward_guidance(adapter, scheduler, unet, cond_embeddings, index, b
                 break
             if ref_ca_saved_attns is None and getattr(unet, "guidance_graphs", True):
                 # forward + energy + backward replayed as one CUDA graph per (layout, prompt) -- built on first use
-                gkey = repr((bboxes, object_positions, keys, sorted(kwargs.items()), loss_scale, cond_embeddings.data_ptr(),
-                             tuple(latents.shape)))
+                # (the layout is baked into the graph by value; the prompt embedding is a static buffer refreshed below)
+                gkey = repr((bboxes, object_positions, keys, sorted(kwargs.items()), loss_scale, tuple(latents.shape),
+                             tuple(cond_embeddings.shape), gb._ip_scale()))
                 graphs = unet.__dict__.setdefault("_guidance_graphs", {})
-                sg = graphs.get(gkey)
+                sg = graphs.pop(gkey, None)
                 if sg is None:
+                    while len(graphs) >= MAX_GUIDANCE_GRAPHS:  # each graph pins its activations (about 2 GB): evict the oldest
+                        graphs.pop(next(iter(graphs)))
                     plan, _ = guidance.build_plan(bboxes, object_positions, keys, index=index, **kwargs)
-                    sg = graphs[gkey] = GuidanceStepGraph(gb, plan, cond_embeddings, loss_scale, tuple(latents.shape))
+                    sg = GuidanceStepGraph(gb, plan, cond_embeddings, loss_scale, tuple(latents.shape))
                     sg.capture(scheduler.scale_model_input(latents, t), t)
+                graphs[gkey] = sg  # most recently used last
                 sg.ctx.copy_(cond_embeddings)
                 loss, grad = sg.replay(scheduler.scale_model_input(latents, t), t)
             else:
