@@ -187,6 +187,10 @@ int tg_guidance_energy(const tg_half* const* maps, tg_half* const* dmaps, const 
                        float fg_weight, float bg_weight, float grad_scale, float ref_eps, float* loss_out,
                        float* workspace, void* stream);
 
+/* y [B,Cout,HW] (NCHW planes) = the first Cout (<= 8) channels of x [B,HW,Cs]: the tail of the UNet's conv_out
+ * (ip_adapter/unet_2d_condition.py:1120) when it runs as tg_conv3x3 with the 4 output channels padded to 64 */
+int tg_nhwc_head_to_nchw(const tg_half* x, tg_half* y, int B, int Cs, int Cout, int HW, void* stream);
+
 /* Tile selection of tg_gemm / tg_conv3x3.  A measured table (tools/gemm_autotune.py -> theatergen_b200/gemm_tuned.json,
  * loaded when the library is opened) overrides the built-in cost model per problem shape: tile width bn in
  * {64,128,160,192,256}, split-K factor 1..8, CTA pairing 0/1; conv != 0 for the implicit-GEMM convolution (K = 9 Cin).

@@ -212,6 +212,8 @@ def test_conv_in_out():
     out2 = ops.conv_out(h, pack_conv3x3(w2), b2)
     ref2 = F.conv2d(h.float().permute(0, 3, 1, 2), w2.float(), b2.float(), padding=1)
     _close(out2, ref2, 2e-3, 2e-3, "conv_out")
+    w64, b64 = ops.pack_conv_out_tc(pack_conv3x3(w2), b2)  # the path TGUNet uses: tensor-core conv, columns padded to 64
+    _close(ops.conv_out_tc(h, w64, b64, 4), ref2, 2e-3, 2e-3, "conv_out_tc")
     h5 = _rand((5, 16, 8, 320), 10)  # pixel count not a multiple of the CTA's 64 pixels x batch
     out5 = ops.conv_out(h5, pack_conv3x3(w2), b2)
     _close(out5, F.conv2d(h5.float().permute(0, 3, 1, 2), w2.float(), b2.float(), padding=1), 2e-3, 2e-3, "conv_out ragged")

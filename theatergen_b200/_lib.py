@@ -32,6 +32,7 @@ _SIGS = {
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),
     "tg_im2col_patch": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "tg_embed_tokens": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, vp]),
+    "tg_nhwc_head_to_nchw": (ci, [vp, vp, ci, ci, ci, ci, vp]),
     "tg_gemm_set_tuned": (ci, [ci, ci, ci, ci, ci, ci, ci, ci]),
     "tg_gemm_clear_tuned": (ci, []),
     "tg_gemm_force_tile": (ci, [ci, ci, ci]),

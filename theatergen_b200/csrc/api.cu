@@ -90,6 +90,10 @@ int tg_im2col_s2(const tg_half* x, int B, int Hh, int W, int C, tg_half* a, int 
   TG_CHECK(x && a, "tg_im2col_s2: null pointer");
   return tg::im2col_s2_nhwc(H(x), B, Hh, W, C, HM(a), pad_lo, ST(stream));
 }
+int tg_nhwc_head_to_nchw(const tg_half* x, tg_half* y, int B, int Cs, int Cout, int HW, void* stream) {
+  TG_CHECK(x && y, "tg_nhwc_head_to_nchw: null pointer");
+  return tg::nhwc_head_to_nchw(H(x), HM(y), B, Cs, Cout, HW, ST(stream));
+}
 int tg_gemm_set_tuned(int M, int N, int K, int act, int conv, int bn, int split, int pair) {
   return tg::gemm_set_tuned(M, N, K, act, conv, bn, split, pair);
 }

@@ -528,6 +528,33 @@ int nchw_to_nhwc(const __half* x, __half* y, int B, int C, int HW, cudaStream_t 
   return 0;
 }
 
+// First Cout (<= 8) channels of a channels-last tensor [B,HW,Cs] as NCHW planes [B,Cout,HW]: the tail of conv_out when it
+// runs on the tensor-core convolution with its 4 output channels padded to a 64-column tile
+// (ip_adapter/unet_2d_condition.py:1120).  One thread per pixel: one 16-byte read, Cout coalesced plane writes.
+__global__ void __launch_bounds__(256)
+nhwc_head_to_nchw_kernel(const __half* __restrict__ x, __half* __restrict__ y, int Cs, int Cout, int HW, size_t total) {
+  grid_dep_launch();
+  grid_dep_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / HW;
+    const int hw = (int)(i - b * HW);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + i * Cs);
+    const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < Cout) y[(b * Cout + c) * HW + hw] = h[c];
+  }
+}
+int nhwc_head_to_nchw(const __half* x, __half* y, int B, int Cs, int Cout, int HW, cudaStream_t st) {
+  TG_CHECK(Cs % 8 == 0 && Cout >= 1 && Cout <= 8 && Cout <= Cs, "nhwc_head_to_nchw: Cs=%d Cout=%d", Cs, Cout);
+  const size_t total = (size_t)B * HW;
+  const int grid = (int)(((total + 255) / 256) < (size_t)(148 * 8) ? ((total + 255) / 256) : (size_t)(148 * 8));
+  TG_CUDA(launch_kernel(nhwc_head_to_nchw_kernel, dim3(grid), dim3(256), 0, st, 1, x, y, Cs, Cout, HW, total));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Fused classifier-free guidance + DDIM step + masked composite, one launch per denoise step
 //   eps    = eps_u + g (eps_c - eps_u)                                  (models/pipelines.py:441-442, 820-821)

@@ -57,6 +57,7 @@ int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half*
 int upsample2x_nhwc(const __half* x, int B, int H, int W, int C, __half* y, cudaStream_t st);
 int im2col_s2_nhwc(const __half* x, int B, int H, int W, int C, __half* a, int pad_lo, cudaStream_t st);
 int im2col_patch(const __half* x, __half* out, int B, int Cin, int H, int W, int P, int Kpad, cudaStream_t st);
+int nhwc_head_to_nchw(const __half* x, __half* y, int B, int Cs, int Cout, int HW, cudaStream_t st);
 int gemm_set_tuned(int M, int N, int K, int act, int conv, int bn, int split, int pair);
 int gemm_clear_tuned();
 int gemm_force_tile(int bn, int split, int pair);

@@ -309,6 +309,27 @@ def conv_out(x_nhwc, w, bias, out=None):
     return out
 
 
+def pack_conv_out_tc(w_packed, bias):
+    """conv_out weights [Cout,3,3,C] (Cout 3 or 4) -> ([64,3,3,C], [64]) zero padded: a 64-column tile of conv3x3."""
+    cout, C = w_packed.shape[0], w_packed.shape[-1]
+    wp = torch.zeros((64, 3, 3, C), dtype=torch.float16, device=w_packed.device)
+    wp[:cout] = w_packed
+    bp = torch.zeros((64,), dtype=torch.float16, device=w_packed.device)
+    bp[:cout] = bias
+    return wp, bp
+
+
+def conv_out_tc(x_nhwc, w64, b64, cout, out=None):
+    """conv_out on the tensor-core convolution: x [B,H,W,C] -> NCHW [B,cout,H,W] (the padded columns are dropped)."""
+    _chk16(x_nhwc, w64, b64, out)
+    B, H, W, _ = x_nhwc.shape
+    y = conv3x3(x_nhwc, w64, b64)
+    if out is None:
+        out = torch.empty((B, cout, H, W), dtype=torch.float16, device=x_nhwc.device)
+    _lib.check(_lib.lib().tg_nhwc_head_to_nchw(_p(y), _p(out), B, 64, cout, H * W, _stream()), "tg_nhwc_head_to_nchw")
+    return out
+
+
 def pointwise_nchw(x, w, bias, out=None):
     """1x1 convolution between tiny channel counts: x NCHW [B,Cin,H,W], w [Cout,Cin] -> NCHW [B,Cout,H,W]."""
     _chk16(x, w, bias, out)
