@@ -247,6 +247,12 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.f + copysignf(e, x));
 }
 
+// 3-input maximum (PTX ISA 8.6, sm_100: one FMNMX3 instead of two FMNMX)
+__device__ __forceinline__ float fmax3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
