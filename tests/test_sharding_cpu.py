@@ -41,7 +41,9 @@ def test_dag_phases_and_assignment():
     shards = [S.shard_dialogues(names, 8, r) for r in range(8)]
     assert all(len(s) == 8 for s in shards) and sorted(sum(shards, [])) == sorted(names)
     # seeds depend on (dialogue index, turn) only -- not on which rank runs the item
-    assert dag["C"][2].bg_seed == S.turn_seeds(3, 2)[0]
+    assert dag["C"][2].bg_seed == S.turn_seeds(3, 2, freeze_dialogue_seed=0)[0] == 3   # generate.py's default: base 0
+    free = S.build_dag("dialogue 4", DIALOGUE4, dialogue_index=3, freeze_dialogue_seed=None)
+    assert free["C"][2].bg_seed == S.turn_seeds(3, 2)[0] == 3 * 4 + 2 + 3
 
 
 def test_cmigbench_shapes_if_present():

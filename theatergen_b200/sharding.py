@@ -53,8 +53,10 @@ class WorkItem:
     deps: list = field(default_factory=list)
 
 
-def build_dag(dialogue_name, dialogue, dialogue_index=0, repeat_ind=0, seed_offset=0):
+def build_dag(dialogue_name, dialogue, dialogue_index=0, repeat_ind=0, seed_offset=0, freeze_dialogue_seed=0):
     """dialogue: {"turn 1": {"objects": [[phrase, [x,y,w,h], obj_id], ...], ...}, ...} (CMIGBench story.json).
+    `freeze_dialogue_seed` defaults to 0 like generate.py's command line (generate.py:45, 209-212: every turn of a
+    dialogue shares the base seed); None selects the turn-counter seeds of the `--freeze_dialogue_seed None` mode.
     Returns {"A": [...], "B": [...], "C": [...]} of WorkItems.  Identical (phrase, obj_id) pairs inside a turn are
     generated once, as theatergen.py:217-226 de-duplicates them."""
     phases = {"A": [], "B": [], "C": []}
@@ -63,7 +65,7 @@ def build_dag(dialogue_name, dialogue, dialogue_index=0, repeat_ind=0, seed_offs
         turn = dialogue.get(f"turn {t + 1}")
         if turn is None:
             continue
-        bg, fg = turn_seeds(dialogue_index, t, repeat_ind, seed_offset)
+        bg, fg = turn_seeds(dialogue_index, t, repeat_ind, seed_offset, freeze_dialogue_seed=freeze_dialogue_seed)
         done_here = set()
         for oi, (phrase, box, obj_id) in enumerate(turn["objects"]):
             if (phrase, obj_id) in done_here:
