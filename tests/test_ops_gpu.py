@@ -249,3 +249,26 @@ def test_cfg_ddim_composite():
     ref2 = frozen.float() * mask.float() + ref * (1 - mask.float())
     _close(l2, ref2, 1.5e-2, 2e-3, "cfg+ddim+composite")
     assert torch.equal(l2[:, :, mask.bool()], frozen[:, :, mask.bool()])
+
+
+@pytest.mark.parametrize("B,N,C", [(10, 4096, 320), (8, 4096, 320), (10, 1024, 640), (3, 1000, 320)])
+def test_cross_attention_query_tile_walk_is_batch_independent(B, N, C):
+    """A CTA of attn_cross_ip_kernel walks 1, 2 or 4 query tiles depending on the launch size (K/V staged once per CTA).
+    Every image of a large batch must come out bit-identical to the same image run alone (one tile per CTA), captured
+    probabilities included; N = 1000 leaves a ragged last tile."""
+    from theatergen_b200 import ops
+    heads, n_text, n_ip = 8, 77, 4
+    T = n_text + n_ip
+    g = torch.Generator().manual_seed(B * 7 + N)
+    q = torch.randn(B * N, C, generator=g).half().cuda()
+    kv = torch.randn(B * T, 4 * C, generator=g).half().cuda()
+    sc = torch.linspace(0.0, 0.9, B).cuda()
+    probs = torch.empty((B, heads, N, n_text), dtype=torch.float16, device="cuda")
+    out = ops.attention_cross_ip(q, kv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:3 * C], kv[:, 3 * C:], B, heads, n_text, n_ip,
+                                 ip_scale=sc, probs=probs)
+    for b in (0, B // 2, B - 1):
+        kvb = kv[b * T:(b + 1) * T]
+        pb = torch.empty((1, heads, N, n_text), dtype=torch.float16, device="cuda")
+        ob = ops.attention_cross_ip(q[b * N:(b + 1) * N], kvb[:, :C], kvb[:, C:2 * C], kvb[:, 2 * C:3 * C], kvb[:, 3 * C:], 1,
+                                    heads, n_text, n_ip, ip_scale=sc[b:b + 1].contiguous(), probs=pb)
+        assert torch.equal(out[b * N:(b + 1) * N], ob) and torch.equal(probs[b], pb[0])

@@ -397,7 +397,7 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
                      const __half* __restrict__ Vt, const __half* __restrict__ Ki, const __half* __restrict__ Vi,
                      int ldkv, int n_text, int n_ip, const float* __restrict__ ip_scale,
                      const __half* __restrict__ add_mask, __half* __restrict__ O, int ldo,
-                     __half* __restrict__ probs, int probs_b0, int Nq, float scale_log2) {
+                     __half* __restrict__ probs, int probs_b0, int Nq, float scale_log2, int qtiles) {
   grid_dep_launch();
   grid_dep_wait();
   using Cfg = CrossCfg<D, NWARPS>;
@@ -409,7 +409,9 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
   __half* sKi = sVt + XT * PITCH;
   __half* sVi = sKi + XI * PITCH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  // A CTA walks `qtiles` consecutive query tiles of its (image, head): the text / image-token K and V (13 KB, more than
+  // a query tile) are staged once, and the next query tile streams in while the current one is computed.
+  const int b = blockIdx.z, h = blockIdx.y, qfirst = blockIdx.x * qtiles * BQ;
   const int T = n_text + n_ip;  // context rows per batch element in the K/V projection buffer
 
   if constexpr (DP != D) {
@@ -419,7 +421,7 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
       *reinterpret_cast<uint4*>(sQ + r * PITCH + c) = make_uint4(0, 0, 0, 0);
     }
   }
-  load_tile<D, PITCH, NT>(sQ, Q + ((size_t)b * Nq + q0) * ldq + h * D, ldq, BQ, min(BQ, Nq - q0), tid);
+  load_tile<D, PITCH, NT>(sQ, Q + ((size_t)b * Nq + qfirst) * ldq + h * D, ldq, BQ, min(BQ, Nq - qfirst), tid);
   load_tile<D, PITCH, NT>(sKt, Kt + (size_t)b * T * ldkv + h * D, ldkv, XT, n_text, tid);
   load_tile<D, PITCH, NT>(sVt, Vt + (size_t)b * T * ldkv + h * D, ldkv, XT, n_text, tid);
   if (n_ip > 0) {
@@ -427,6 +429,10 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
     load_tile<D, PITCH, NT>(sVi, Vi + ((size_t)b * T + n_text) * ldkv + h * D, ldkv, XI, n_ip, tid);
   }
   cp_async_commit();
+
+  for (int t = 0; t < qtiles; ++t) {
+  const int q0 = qfirst + t * BQ;
+  if (q0 >= Nq) break;
   cp_async_wait<0>();
   __syncthreads();
 
@@ -434,6 +440,11 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
 #pragma unroll
   for (int ks = 0; ks < DP / 16; ++ks)
     ldsm_x4(qf[ks], sQ + (warp * 16 + (lane & 15)) * PITCH + ks * 16 + (lane >> 4) * 8);
+  if (t + 1 < qtiles && q0 + BQ < Nq) {  // every warp holds its Q fragments: the staging buffer takes the next tile
+    __syncthreads();
+    load_tile<D, PITCH, NT>(sQ, Q + ((size_t)b * Nq + q0 + BQ) * ldq + h * D, ldq, BQ, min(BQ, Nq - q0 - BQ), tid);
+    cp_async_commit();
+  }
 
   float o[DT][4];
 #pragma unroll
@@ -456,6 +467,7 @@ attn_cross_ip_kernel(const __half* __restrict__ Q, int ldq, const __half* __rest
     if (row0 < Nq) *reinterpret_cast<__half2*>(gO + (size_t)row0 * ldo + c) = __floats2half2_rn(o[i][0], o[i][1]);
     if (row1 < Nq) *reinterpret_cast<__half2*>(gO + (size_t)row1 * ldo + c) = __floats2half2_rn(o[i][2], o[i][3]);
   }
+  }  // query tiles of this CTA
 }
 
 template <int D, int NWARPS>
@@ -470,9 +482,13 @@ static int launch_cross(const __half* Q, int ldq, const __half* Kt, const __half
     TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
     attr = true;
   }
-  dim3 grid((Nq + Cfg::BQ - 1) / Cfg::BQ, heads, B);
+  // query tiles per CTA: 2 or 4 while at least ~8 CTAs per SM remain (the K/V staging is then shared by more queries)
+  const int tiles = (Nq + Cfg::BQ - 1) / Cfg::BQ;
+  int qtiles = 1;
+  while (qtiles < 4 && tiles % (2 * qtiles) == 0 && (tiles / (2 * qtiles)) * heads * B >= 148 * 8) qtiles *= 2;
+  dim3 grid((tiles + qtiles - 1) / qtiles, heads, B);
   TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, ldq, Kt, Vt, Ki, Vi, ldkv, n_text, n_ip, ip_scale, add_mask, O, ldo,
-                                             probs, probs_b0, Nq, scale * 1.4426950408889634f));
+                                             probs, probs_b0, Nq, scale * 1.4426950408889634f, qtiles));
   TG_COUNT_LAUNCH();
   TG_LAUNCH_CHECK();
   return 0;
