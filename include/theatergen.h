@@ -12,6 +12,12 @@
  *     passed as void*), never synchronises, and is CUDA-graph capturable.
  *   - activations are channels-last: an image tensor is [B, H, W, C]; a token tensor is [B*N, C].
  *   - there is no CPU fallback: without an sm_100a device every call fails.
+ *   - process model: ONE PROCESS PER GPU (the launch model of bench.py / torch.distributed), one host thread issuing
+ *     calls per device at a time.  The library keeps per-device state only where stated (the split-K workspace of
+ *     tg_gemm / tg_conv3x3, keyed by (device, slot); kernel attributes are set once per (kernel, device)), so a process
+ *     that drives several devices works as long as each device is driven by one thread at a time; concurrent host
+ *     threads on the SAME device are not supported (tg_gemm_set_scratch_slot is per calling thread, the workspace
+ *     of a slot is not locked).
  */
 #ifndef THEATERGEN_H_
 #define THEATERGEN_H_

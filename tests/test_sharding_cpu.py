@@ -46,6 +46,27 @@ def test_dag_phases_and_assignment():
     assert free["C"][2].bg_seed == S.turn_seeds(3, 2)[0] == 3 * 4 + 2 + 3
 
 
+def test_duplicates_follow_the_reference_rule():
+    """theatergen.py:217-226: only a repeat of the IMMEDIATELY previous (prompt, obj_id) is skipped (its slot aliases
+    the previous outputs); a non-consecutive repeat is generated again, by then with the id's reference image."""
+    d = {"turn 1": {"objects": [["a fox", [0, 0, 100, 100], 1], ["a fox", [50, 0, 100, 100], 1],      # consecutive
+                                ["an owl", [200, 0, 100, 100], 2], ["a fox", [300, 0, 100, 100], 1],  # non-consecutive
+                                ["a fox", [300, 50, 100, 100], 5]]},                                   # same phrase, new id
+         "turn 3": {"objects": [["a fox", [0, 0, 100, 100], 1]]}}                                      # turn 2 missing
+    dag = S.build_dag("d", d, dialogue_index=2, freeze_dialogue_seed=None)
+    assert [(i.turn, i.obj_index, i.obj_id) for i in dag["A"]] == [(0, 0, 1), (0, 2, 2), (0, 4, 5)]
+    assert [(i.turn, i.obj_index, i.obj_id, i.ip_scale) for i in dag["B"]] == [(0, 3, 1, 0.4), (2, 0, 1, 0.4)]
+    assert [(i.turn, i.obj_index, i.alias_of) for i in dag["alias"]] == [(0, 1, 0)]
+    assert [i.phase for i in dag["turns"][0]] == ["A", "alias", "A", "B", "A"]       # every slot has a placeholder
+    assert len(dag["C"]) == 2 and [c.turn for c in dag["C"]] == [0, 2]
+    # `ind` counts turns that exist (generate.py:195-198 skips a missing turn before `ind += 1`): dialogue index 2 with
+    # 4-turn predecessors -> turns_before 8, 9 ; ind_offset = seed_offset (0) + finished dialogues (2)
+    assert [c.bg_seed for c in dag["C"]] == [8 + 2, 9 + 2]
+    short = S.build_dag("d", d, dialogue_index=2, freeze_dialogue_seed=None, turns_before_dialogue=5)
+    assert [c.bg_seed for c in short["C"]] == [5 + 2, 6 + 2]
+    assert S.count_turns(d) == 2
+
+
 def test_cmigbench_shapes_if_present():
     p = "/root/reference/CMIGBench/story.json"
     if not os.path.exists(p):

@@ -244,11 +244,7 @@ static int launch_self(const __half* Q, const __half* K, const __half* V, int ld
                        int ldo, int B, int heads, int Nq, int Nk, float scale, int causal, cudaStream_t st) {
   using Cfg = SelfCfg<D, NWARPS>;
   auto kern = attn_self_kernel<D, NWARPS>;
-  static bool attr = false;
-  if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
-  }
+  TG_SMEM_ATTR_ONCE(kern, Cfg::SMEM);
   dim3 grid((Nq + Cfg::BQ - 1) / Cfg::BQ, heads, B);
   TG_CUDA(launch_kernel(kern, dim3(grid), dim3(NWARPS * 32), Cfg::SMEM, st, 1, Q, K, V, ldq, ldk, ldv, O, ldo, Nq, Nk, scale * 1.4426950408889634f, causal));
   TG_COUNT_LAUNCH();
@@ -477,11 +473,7 @@ static int launch_cross(const __half* Q, int ldq, const __half* Kt, const __half
                         int Nq, float scale, cudaStream_t st) {
   using Cfg = CrossCfg<D, NWARPS>;
   auto kern = attn_cross_ip_kernel<D, NWARPS>;
-  static bool attr = false;
-  if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
-  }
+  TG_SMEM_ATTR_ONCE(kern, Cfg::SMEM);
   // query tiles per CTA: 2 or 4 while at least ~8 CTAs per SM remain (the K/V staging is then shared by more queries)
   const int tiles = (Nq + Cfg::BQ - 1) / Cfg::BQ;
   int qtiles = 1;

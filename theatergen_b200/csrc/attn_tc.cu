@@ -370,11 +370,7 @@ static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int
                           int B, int heads, int N, int d, float scale, cudaStream_t st) {
   using Cfg = AttnCfg<CH>;
   auto kern = attn_tc_kernel<CH>;
-  static bool attr = false;
-  if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr = true;
-  }
+  TG_SMEM_ATTR_ONCE(kern, Cfg::SMEM);
   CUtensorMap tk, tv;
   const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * CH * ATD;
   if (make_tmap_2d(&tk, K, rows, cols, ldk, AT_TPS * ATK)) return -1;

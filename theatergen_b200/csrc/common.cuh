@@ -33,6 +33,21 @@ const char* get_error();
     }                                                                              \
   } while (0)
 
+// cudaFuncSetAttribute applies to the CURRENT device's copy of a kernel: opt in to the dynamic shared memory once per
+// (kernel instantiation, device) -- a process that drives a second device must not inherit the first one's flag.
+#define TG_MAX_DEVICES 16
+#define TG_SMEM_ATTR_ONCE(kern, bytes)                                                                    \
+  do {                                                                                                    \
+    static bool _done[TG_MAX_DEVICES] = {};                                                               \
+    int _dev = 0;                                                                                         \
+    TG_CUDA(cudaGetDevice(&_dev));                                                                        \
+    TG_CHECK(_dev >= 0 && _dev < TG_MAX_DEVICES, "device index %d out of range", _dev);                    \
+    if (!_done[_dev]) {                                                                                   \
+      TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      _done[_dev] = true;                                                                                 \
+    }                                                                                                     \
+  } while (0)
+
 #define TG_LAUNCH_CHECK()                                                          \
   do {                                                                             \
     cudaError_t _e = cudaGetLastError();                                           \

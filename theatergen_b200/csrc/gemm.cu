@@ -703,12 +703,8 @@ template <int BN, int STAGES, bool PAIR, bool KY3 = false>
 static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __half* Wt, const CUtensorMap& c,
                        GemmArgs g, const DeviceScratch& sc, cudaStream_t st) {
   using L = GemmSmem<BN, STAGES, PAIR, KY3>;
-  static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, STAGES, PAIR, KY3>;
-  if (!attr_set) {
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
+  TG_SMEM_ATTR_ONCE(kern, L::TOTAL);
   CUtensorMap b;
   if (KY3) {
     if (make_tmap_w_ky3(&b, Wt, g.N, g.Cin, BN / 2)) return -1;

@@ -115,11 +115,7 @@ static int conv_in_launch(const __half* x, const __half* w, const __half* bias, 
   constexpr int PIX = 32;
   const size_t smem = (size_t)(CIN * 9 * Cout + PIX * CIN * 9) * sizeof(float);
   auto kern = conv_in_kernel<CIN, PIX>;
-  static bool attr = false;
-  if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
+  TG_SMEM_ATTR_ONCE(kern, 96 * 1024);
   TG_CHECK(smem <= 96 * 1024, "conv_in: Cout=%d too large", Cout);
   TG_CUDA(launch_kernel(kern, dim3((H * W + PIX - 1) / PIX, B), dim3(256), smem, st, 1, x, w, bias, y, H, W, Cout, silu));
   TG_COUNT_LAUNCH();
@@ -215,11 +211,7 @@ template <int COUT>
 static int conv_out_launch(const __half* x, const __half* w, const __half* bias, __half* y, int B, int H, int W, int C,
                            cudaStream_t st) {
   const size_t smem = (size_t)COUT * 9 * C * 2;
-  static bool attr = false;
-  if (!attr) {
-    TG_CUDA(cudaFuncSetAttribute(conv_out_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr = true;
-  }
+  TG_SMEM_ATTR_ONCE(conv_out_kernel<COUT>, 96 * 1024);
   TG_CHECK(smem <= 96 * 1024, "conv_out: C=%d too large", C);
   const int total = B * H * W;
   TG_CUDA(launch_kernel(conv_out_kernel<COUT>, dim3((total + CONV_OUT_PIX - 1) / CONV_OUT_PIX), dim3(256), smem, st, 1, x, w, bias, y, B, H, W, C));

@@ -336,7 +336,11 @@ int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, in
   const int C = C1 + C2;
   TG_CHECK(C % GN_GROUPS == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN_THREADS, "groupnorm: C1=%d C2=%d unsupported", C1, C2);
   TG_CHECK(B <= GN_MAX_BATCH, "groupnorm: batch %d > %d", B, GN_MAX_BATCH);
-  static bool attr = false;
+  static bool attr_dev[TG_MAX_DEVICES] = {};
+  int cur_dev = 0;
+  TG_CUDA(cudaGetDevice(&cur_dev));
+  TG_CHECK(cur_dev >= 0 && cur_dev < TG_MAX_DEVICES, "device index %d out of range", cur_dev);
+  bool& attr = attr_dev[cur_dev];
   if (!attr) {
     TG_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     TG_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN_FUSED_MAX_SMEM));

@@ -197,5 +197,5 @@ class DenoiseEngine:
                 trace_host[i + 1].copy_(cur.trace, non_blocking=True)
             if on_step is not None:
                 on_step(i, cur)
-        final = (sg_plain or sg).latents
-        return final
+        # the step graph owns its `latents` buffer and the next call with the same shape overwrites it: hand out a copy
+        return (sg_plain or sg).latents.clone()

@@ -77,7 +77,12 @@ class IPAdapter:
     def set_ip_adapter(self):
         unet = self.pipe.unet
         if isinstance(unet, TGUNet):
-            return  # module-level drop-in: the handles are already in unet.attn_processors
+            # module-level drop-in: the handles are already in unet.attn_processors; the context split (text | image
+            # tokens, attention_processor.py:467-471) is fixed when the UNet is packed
+            if unet.num_ip_tokens != self.num_tokens:
+                raise RuntimeError(f"TGUNet was built for {unet.num_ip_tokens} image tokens, the adapter has "
+                                   f"{self.num_tokens}: construct TGUNet(state_dict, num_ip_tokens={self.num_tokens})")
+            return
         attn_procs = {}
         for name in unet.attn_processors.keys():  # same naming logic as ip_adapter/ip_adapter.py:98-116
             cross = None if name.endswith("attn1.processor") else unet.config.cross_attention_dim

@@ -20,7 +20,7 @@ def encode_prompts(tokenizer, text_encoder, prompts, negative_prompt="", return_
     """-> (uncond [1|n,77,768], cond [n,77,768]) when `one_uncond_input_only`, else (cat, uncond, cond) or just cat."""
     if negative_prompt == "":
         print("Note that negative_prompt is an empty string")
-    prompts = list(prompts)
+    prompts = [prompts] if isinstance(prompts, str) else list(prompts)  # the tokenizer accepts a bare string too
     cond_ids = tokenizer(prompts, padding="max_length", max_length=tokenizer.model_max_length, truncation=True,
                          return_tensors="pt").input_ids
     n_uncond = 1 if one_uncond_input_only else len(prompts)

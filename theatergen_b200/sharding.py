@@ -22,15 +22,24 @@ LARGE_CONSTANT3 = 6789       # generate.py:159
 
 
 def turn_seeds(dialogue_index, turn_index, repeat_ind=0, seed_offset=0, n_dialogues=None, regenerate_ind=0,
-               freeze_dialogue_seed=None, turns_per_dialogue=4):
-    """(bg_seed, fg_seed_start) of generate.py:209-243 for a fresh run (no resume skips): `ind` counts turns globally,
-    `seed_offset` grows by one per finished dialogue (generate.py:262)."""
+               freeze_dialogue_seed=None, turns_per_dialogue=4, turns_before=None):
+    """(bg_seed, fg_seed_start) of generate.py:209-243 for a fresh run (no resume skips).  `seed_offset` grows by one
+    per finished dialogue (generate.py:262).  `ind` (the seed base of the `--freeze_dialogue_seed None` mode) counts
+    the turns that EXIST: generate.py:195-198 `continue`s past a missing turn before `ind += 1` (:260) is reached.
+    `turns_before` = number of existing turns generated before this one (all earlier dialogues + earlier turns of this
+    dialogue); the default assumes `turns_per_dialogue` turns in every earlier dialogue and none missing before
+    `turn_index` -- true for every CMIGBench dialogue (4000 x 4 turns)."""
     done_dialogues = dialogue_index + (regenerate_ind * n_dialogues if regenerate_ind else 0)
-    ind = done_dialogues * turns_per_dialogue + turn_index
+    ind = done_dialogues * turns_per_dialogue + turn_index if turns_before is None else turns_before
     base = freeze_dialogue_seed if freeze_dialogue_seed is not None else ind
     ind_offset = repeat_ind * LARGE_CONSTANT3 + seed_offset + done_dialogues
     bg_seed = base + ind_offset
     return bg_seed, bg_seed + LARGE_CONSTANT
+
+
+def count_turns(dialogue):
+    """turns generate.py's loop finds in a dialogue record (`for turn in ['turn 1'..'turn 4']`, generate.py:191-198)"""
+    return sum(1 for t in range(4) if f"turn {t + 1}" in dialogue)
 
 
 def shard_dialogues(names, world, rank):
@@ -40,7 +49,7 @@ def shard_dialogues(names, world, rank):
 
 @dataclass
 class WorkItem:
-    phase: str            # "A" | "B" | "C"
+    phase: str            # "A" | "B" | "C" | "alias"
     dialogue: str
     turn: int             # 0-based
     obj_index: int = -1   # position inside the turn's object list (-1 for phase C)
@@ -51,31 +60,49 @@ class WorkItem:
     bg_seed: int = 0
     fg_seed_start: int = 0
     deps: list = field(default_factory=list)
+    alias_of: int = -1    # phase "alias": obj_index (same turn) of the item whose outputs this position repeats
 
 
-def build_dag(dialogue_name, dialogue, dialogue_index=0, repeat_ind=0, seed_offset=0, freeze_dialogue_seed=0):
+def build_dag(dialogue_name, dialogue, dialogue_index=0, repeat_ind=0, seed_offset=0, freeze_dialogue_seed=0,
+              turns_before_dialogue=None):
     """dialogue: {"turn 1": {"objects": [[phrase, [x,y,w,h], obj_id], ...], ...}, ...} (CMIGBench story.json).
     `freeze_dialogue_seed` defaults to 0 like generate.py's command line (generate.py:45, 209-212: every turn of a
-    dialogue shares the base seed); None selects the turn-counter seeds of the `--freeze_dialogue_seed None` mode.
-    Returns {"A": [...], "B": [...], "C": [...]} of WorkItems.  Identical (phrase, obj_id) pairs inside a turn are
-    generated once, as theatergen.py:217-226 de-duplicates them."""
-    phases = {"A": [], "B": [], "C": []}
+    dialogue shares the base seed); None selects the turn-counter seeds of the `--freeze_dialogue_seed None` mode
+    (`turns_before_dialogue` = existing turns of all earlier dialogues; default 4 per dialogue).
+    Returns {"A": [...], "B": [...], "C": [...], "alias": [...], "turns": {t: [item per object, in order]}}.
+
+    Duplicates follow theatergen.py:217-226 exactly: an object is skipped only when the IMMEDIATELY PREVIOUS object of
+    the turn has the same (prompt, obj_id) -- its slot then repeats the previous slot's outputs (an "alias" item, no
+    work).  A non-consecutive repeat is generated again; by then the id's reference image exists (the sequential
+    reference wrote it at the first occurrence, models/pipelines.py:476-477), so it is a phase-B item at scale 0.4.
+    The per-object prompt is a function of the phrase alone inside a turn (parse.convert_spec), so (phrase, obj_id)
+    stands for (prompt, obj_id).  Every work item of an id -- phase A included -- is keyed by (turn, obj_index)."""
+    phases = {"A": [], "B": [], "C": [], "alias": [], "turns": {}}
     seen = set()
+    n_before = (dialogue_index * 4 if turns_before_dialogue is None else turns_before_dialogue)
     for t in range(4):
         turn = dialogue.get(f"turn {t + 1}")
         if turn is None:
             continue
-        bg, fg = turn_seeds(dialogue_index, t, repeat_ind, seed_offset, freeze_dialogue_seed=freeze_dialogue_seed)
-        done_here = set()
+        bg, fg = turn_seeds(dialogue_index, t, repeat_ind, seed_offset, freeze_dialogue_seed=freeze_dialogue_seed,
+                            turns_before=n_before)
+        n_before += 1
+        prev, prev_index, slots = None, -1, []
         for oi, (phrase, box, obj_id) in enumerate(turn["objects"]):
-            if (phrase, obj_id) in done_here:
+            if prev == (phrase, obj_id):
+                it = WorkItem("alias", dialogue_name, t, oi, obj_id, phrase, tuple(box), bg_seed=bg, fg_seed_start=fg,
+                              alias_of=prev_index)
+                phases["alias"].append(it)
+                slots.append(it)
                 continue
-            done_here.add((phrase, obj_id))
+            prev, prev_index = (phrase, obj_id), oi
             first = obj_id not in seen
             seen.add(obj_id)
-            phases["A" if first else "B"].append(WorkItem(
-                "A" if first else "B", dialogue_name, t, oi, obj_id, phrase, tuple(box), 0.0 if first else 0.4, bg, fg,
-                deps=[] if first else [("A", obj_id)]))
+            it = WorkItem("A" if first else "B", dialogue_name, t, oi, obj_id, phrase, tuple(box),
+                          0.0 if first else 0.4, bg, fg, deps=[] if first else [("A", obj_id)])
+            phases[it.phase].append(it)
+            slots.append(it)
+        phases["turns"][t] = slots
         phases["C"].append(WorkItem("C", dialogue_name, t, ip_scale=0.1, bg_seed=bg, fg_seed_start=fg,
                                     deps=[("stage1", t)]))
     return phases

@@ -102,7 +102,7 @@ def pack_resnet(g, sd, p, cin, co, temb_off):
     return r, g(p + ".time_emb_proj.weight"), g(p + ".time_emb_proj.bias")
 
 
-def pack_transformer(g, dev, p, c, key, kv_off, has_ip):
+def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
     """Transformer2DModel + BasicTransformerBlock parameters -> kernel layouts; returns (dict, context K/V rows)."""
     tb_ = p + ".transformer_blocks.0"
     t = dict(C=c, key=key, kv_off=kv_off)
@@ -129,7 +129,12 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip):
     t["o2w"], t["o2b"] = g(f"{tb_}.attn2.to_out.0.weight"), g(f"{tb_}.attn2.to_out.0.bias")
     rows = [g(f"{tb_}.attn2.to_k.weight"), g(f"{tb_}.attn2.to_v.weight")]
     if has_ip:
-        rows += [g(f"{tb_}.attn2.processor.to_k_ip.weight"), g(f"{tb_}.attn2.processor.to_v_ip.weight")]
+        # the IP-Adapter rows always exist when the UNet is built for image tokens: a stock diffusers state dict has no
+        # to_k_ip / to_v_ip keys -- they arrive later through IPAdapter.load_ip_adapter -> TGUNet.load_ip_weights
+        # (ip_adapter/ip_adapter.py:127-140); zero rows until then (an unloaded adapter contributes nothing)
+        for n_ in ("to_k_ip", "to_v_ip"):
+            k_ = f"{tb_}.attn2.processor.{n_}.weight"
+            rows.append(g(k_) if has_key(k_) else torch.zeros_like(rows[0]))
     t["kv_rows"] = len(rows)
     t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
     t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
@@ -266,10 +271,10 @@ class TGUNet(_BlockNet):
         w["temb.w"], w["temb.b"] = torch.cat(tw, 0).contiguous(), torch.cat(tb, 0).contiguous()
         self.transformers = {}
         kvw, off = [], 0
-        has_ip = any(k.endswith("processor.to_k_ip.weight") for k in sd)
+        has_ip = self.num_ip_tokens > 0
         self.has_ip = has_ip
         for p, c, key in _transformer_specs():
-            self.transformers[p], rows = pack_transformer(g, dev, p, c, key, off, has_ip)
+            self.transformers[p], rows = pack_transformer(g, dev, p, c, key, off, has_ip, sd.__contains__)
             kvw += rows
             off += c * len(rows)
         w["ctxkv.w"] = torch.cat(kvw, 0).contiguous()
@@ -291,7 +296,7 @@ class TGUNet(_BlockNet):
         """`ip_adapter.{1,3,..,31}.to_{k,v}_ip.weight` in processor order (down, up, mid -- the order of
         unet.attn_processors the reference loads through a ModuleList, ip_adapter/ip_adapter.py:139-140)."""
         if not self.has_ip:
-            raise RuntimeError("TGUNet was packed without IP-Adapter rows; construct it with to_k_ip/to_v_ip keys")
+            raise RuntimeError("TGUNet was built with num_ip_tokens=0: it has no IP-Adapter rows to load into")
         for n, (p, c, _) in enumerate(_transformer_specs()):
             idx = 2 * n + 1
             o = self.transformers[p]["kv_off"]

@@ -22,6 +22,9 @@ class EnergyPlan:
 
     def __init__(self, bboxes, object_positions, guidance_attn_keys, fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0,
                  bg_weight=1.0, ref_positions=None, ref_ca_loss_weight=1.0, use_ratio_based_loss=False, **unused):
+        # Deviation from the reference's DEFAULT, on purpose: add_ca_loss_per_attn_map_to_loss defaults to
+        # use_ratio_based_loss=True (utils/guidance.py:91), but every caller in the reference passes False explicitly
+        # (theatergen.py:367, 430) and the ratio branch is marked deprecated there; here False is the default and True raises.
         if use_ratio_based_loss:
             raise NotImplementedError("ratio-based loss is deprecated in the reference (utils/guidance.py:122) and "
                                       "never selected by theatergen.py; only the max-based energy is implemented")

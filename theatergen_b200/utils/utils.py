@@ -76,8 +76,10 @@ def binary_mask_to_center(mask, normalize=False):
     h, w = mask.shape
     total = mask.sum()
     if isinstance(mask, torch.Tensor):
-        x_coord = ((mask.sum(dim=0) @ torch.arange(w, device=mask.device)) / total).item()
-        y_coord = ((mask.sum(dim=1) @ torch.arange(h, device=mask.device)) / total).item()
+        # the reference's integer dot product (`mask.sum(dim=0) @ arange`, utils/utils.py:107-108) written as mul + sum:
+        # same exact int64 value, and defined for integer tensors on a CUDA device as well
+        x_coord = (((mask.sum(dim=0) * torch.arange(w, device=mask.device)).sum()) / total).item()
+        y_coord = (((mask.sum(dim=1) * torch.arange(h, device=mask.device)).sum()) / total).item()
     else:
         x_coord = (mask.sum(axis=0) @ np.arange(w)) / total
         y_coord = (mask.sum(axis=1) @ np.arange(h)) / total
