@@ -20,7 +20,19 @@ energy apply to the stage-2 trajectory only): in steady state a rank always hold
 dialogue's turn in stage 2 (config 5: 8 dialogues per GPU), and co-batching them is a scheduling decision, not a
 change of arithmetic.  `--separate-stage2` runs the two forwards as separate graphs (B=8 then B=2) instead.
 The stage-2 ControlNet (reference models/pipelines.py:770-778) runs on our kernels inside the same
-graph; its timestep-independent conditioning embedder runs once per trajectory (at index 0, inside the timed region).
+graph; its timestep-independent conditioning embedder runs once per trajectory, at timestep index 0.  The timed region
+STARTS at index 0 (the warm-up steps are the last indices of the previous trajectory), so the embedder, the per-trajectory
+host->device copies of the e2e leg and the energy-carrying indices (< 30) are inside every timed window.
+
+Extra keys next to the contract's (all computed outside the timed region, rank 0, N = 1):
+  parity               the 50-step trajectories of this very workload (the co-batched graphs that were timed) against the
+                       oracle loops run in fp32 on the same GPU, with the oracle's fp16 run (the reference's numerics) as
+                       the noise floor: max-abs latent drift, per step and final; guidance energy at step 0.
+  gpu_eager_reference  the oracle -- the reference's op structure, materialised attention probabilities and all -- run by
+                       PyTorch eager fp16 (cuBLAS / cuDNN) on this GPU: forward times and the reference's loop with its
+                       per-step latents.cpu() ("the number to beat").
+  sustained            the same device-resident step loop run for >= 3 s (250 steps = five 50-step trajectories).
+The oracle is the checker in those legs, never the thing measured as ours.
 """
 import argparse
 import json
@@ -127,6 +139,135 @@ def run_reference(args):
 
 
 # =============================================================================================================
+# checker legs (outside every timed region): 50-step parity against the oracle, same-GPU eager reference timing
+# =============================================================================================================
+def parity_leg(torch, dev, gme, gm, embed_hint, d_hint, d_ts, d_coef, d_frozen, h_latm, sdu, sdc, ctx1, ctx2, lat1, lat2,
+               ctrl_ctx, mask, bboxes, K, STEPS):
+    """Runs the timed workload itself (co-batched B=10 graphs: 4 stage-1 characters + the stage-2 trajectory with
+    ControlNet, composite, capture, energy) for one full 50-step trajectory and compares every step's latents with the
+    oracle's loops (oracle/parity.py: fp32 = the yardstick, fp16 = the reference's own numerics)."""
+    from oracle import parity as P
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    gme.latents.copy_(h_latm)
+    trace = [gme.latents.clone()]
+    energies = []
+    for idx in range(STEPS):
+        if idx == 0:
+            embed_hint(d_hint)
+        g = gme if idx < 30 else gm
+        g.t.copy_(d_ts[idx].expand(2 * (K + 1))); g.coef.copy_(d_coef[idx]); g.frozen.copy_(d_frozen[idx + 1])
+        g.replay()
+        if idx == 29:
+            gm.latents.copy_(gme.latents)
+        trace.append(g.trace.clone())
+        if idx < 30:
+            energies.append(gme.loss.clone())
+    torch.cuda.synchronize()
+    ours = torch.stack(trace)                                   # [51, K+1, 4, 64, 64]
+    energies = [e.item() for e in energies]
+    scales = [0.0, 0.4, 0.4, 0.4]
+    en = dict(bboxes=bboxes, positions=[[5, 6], [9], [12, 13, 14], [17]], upto=30,
+              kwargs=dict(fg_top_p=0.2, bg_top_p=0.2, fg_weight=1.0, bg_weight=4.0))
+    out = {}
+    t0 = time.perf_counter()
+    refs = {}
+    for name, dt in (("fp32", torch.float32), ("fp16", torch.float16)):
+        r1 = P.stage1_traces(sdu, lat1.to(dev), ctx1.to(dev), scales, STEPS, dt)
+        r2, e2 = P.stage2_trace(sdu, sdc, lat2.to(dev), ctx2.to(dev), ctrl_ctx.to(dev), d_hint, d_frozen, mask.to(dev),
+                                STEPS, STEPS, dt, energy=en)
+        refs[name] = (torch.cat([r1, r2], 1), e2)
+    s = P.summarize(ours, refs["fp32"][0], refs["fp16"][0])
+    s1 = P.summarize(ours[:, :K], refs["fp32"][0][:, :K], refs["fp16"][0][:, :K])
+    s2 = P.summarize(ours[:, K:], refs["fp32"][0][:, K:], refs["fp16"][0][:, K:])
+    e32, e16 = refs["fp32"][1], refs["fp16"][1]
+    rel = lambda a, b: max(abs(x - y) / max(abs(y), 1e-6) for x, y in zip(a, b))  # noqa: E731
+    out.update({k: s[k] for k in ("steps", "trajectories", "max_abs_latent_vs_fp32_oracle", "fp16_oracle_gap",
+                                  "first_step_max_abs", "first_step_fp16_oracle_gap", "final_max_abs",
+                                  "final_fp16_oracle_gap", "rms_final", "rms_final_fp16_oracle")})
+    out["stage1_4chars"] = {"max_abs": s1["max_abs_latent_vs_fp32_oracle"], "fp16_oracle_gap": s1["fp16_oracle_gap"]}
+    out["stage2_controlnet_composite"] = {"max_abs": s2["max_abs_latent_vs_fp32_oracle"],
+                                          "fp16_oracle_gap": s2["fp16_oracle_gap"]}
+    out["per_step_max_abs_every_5"] = s["per_step_max_abs"][::5]
+    out["per_step_fp16_oracle_gap_every_5"] = s["per_step_fp16_oracle_gap"][::5]
+    out["guidance_energy"] = {"step0_ours": energies[0], "step0_fp32_oracle": e32[0],
+                              "max_rel_diff_30_steps": rel(energies, e32), "fp16_oracle_max_rel_diff": rel(e16, e32)}
+    out["north_star_tolerance"] = "1e-3 max-abs on latents"
+    out["what"] = ("max over steps / trajectories / elements of |latents - fp32 oracle| for the timed co-batched workload "
+                   "(fp16 storage, fp32 accumulate); fp16_oracle_gap = the same for the oracle run in fp16, i.e. the "
+                   "reference's own arithmetic on this GPU")
+    out["oracle_seconds"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+def eager_reference_leg(torch, dev, sdu, sdc, ctx1, ctx2, lat1, lat2, ctrl_ctx, d_hint, d_frozen, mask, K):
+    """the oracle -- the reference's op sequence (baddbmm -> softmax -> bmm attention with materialised
+    probabilities, unfused norms, NCHW convolutions) -- executed by PyTorch eager fp16 on this GPU, with the reference's
+    per-step `latents.cpu()` (models/pipelines.py:449-453, 835).  One bench step of the reference = the 4 characters'
+    stage-1 steps one after the other (B=2 each; the reference cannot co-batch: its IP scale is a module attribute) + one
+    stage-2 step (ControlNet + UNet B=2 + composite)."""
+    from oracle import controlnet as OC
+    from oracle import ddim as OD
+    from oracle import unet as OU
+    u16 = {k: v.half() for k, v in sdu.items()}
+    c16 = {k: v.half() for k, v in sdc.items()}
+    sched = OD.DDIM()
+    sched.set_timesteps(50)
+    ts = [int(t) for t in sched.timesteps]
+    scales = [0.0, 0.4, 0.4, 0.4]
+    lat = [lat1[k:k + 1].to(dev) for k in range(K)] + [lat2.to(dev)]
+    cx = [torch.stack([ctx1[k], ctx1[K + k]]).to(dev) for k in range(K)] + [ctx2.to(dev)]
+    cc, cond = ctrl_ctx.to(dev), d_hint.repeat(2, 1, 1, 1)
+    fm = mask.to(dev).half()
+    host = []
+
+    def fwd_ms(B, reps=5):
+        g = torch.Generator().manual_seed(B)
+        x = torch.randn(B, 4, 64, 64, generator=g).half().to(dev)
+        c = torch.randn(B, 81, 768, generator=g).half().to(dev)
+        for _ in range(2):
+            OU.unet_forward(u16, x, 501, c, ip_scale=0.4)
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(reps):
+            OU.unet_forward(u16, x, 501, c, ip_scale=0.4)
+        e_.record()
+        torch.cuda.synchronize()
+        return round(s_.elapsed_time(e_) / reps, 3)
+
+    def bench_step(i):
+        t = ts[i % 50]
+        for k in range(K):
+            eps = OU.unet_forward(u16, torch.cat([lat[k]] * 2), t, cx[k], ip_scale=scales[k])
+            lat[k] = sched.step(OD.cfg(eps, 7.5), t, lat[k])
+            host.append(lat[k].cpu())
+        x = torch.cat([lat[K]] * 2)
+        d, m = OC.controlnet_forward(c16, x, t, cc, cond)
+        eps = OU.unet_forward(u16, x, t, cx[K], ip_scale=0.1, down_residuals=d, mid_residual=m)
+        l2 = sched.step(OD.cfg(eps, 7.5), t, lat[K])
+        lat[K] = d_frozen[(i % 50) + 1] * fm + l2 * (1.0 - fm)
+        host.append(lat[K].cpu())
+
+    with torch.no_grad():
+        f2, f10 = fwd_ms(2), fwd_ms(10, 3)
+        n, warm = 10, 2
+        for i in range(warm):
+            bench_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(warm, warm + n):
+            bench_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": round((K + 1) * n / dt, 2), "unit": "steps/s", "ms_per_bench_step": round(1e3 * dt / n, 3),
+            "bench_steps_timed": n, "unet_forward_ms_B2": f2, "unet_forward_ms_B10": f10, "dtype": "f16",
+            "what": "oracle (reference op structure) in PyTorch eager fp16 on this GPU: 4 sequential B=2 stage-1 steps + "
+                    "1 stage-2 step (ControlNet + UNet + composite) per bench step, latents.cpu() after every denoise "
+                    "step like the reference; no guidance energy (the reference never evaluates it)"}
+
+
+# =============================================================================================================
 # our arm
 # =============================================================================================================
 def build_inputs(torch, dev, K=4):
@@ -172,8 +313,9 @@ def run_ours(args):
                 off += v.numel()
         return sd
 
-    net = TGUNet(shared(synth.synth_state_dict(dev, 1234, fill=(rank == 0))), dev)
-    cnet = TGControlNet(shared(synth.synth_controlnet_state_dict(dev, 4321, fill=(rank == 0))), dev)
+    sdu = shared(synth.synth_state_dict(dev, 1234, fill=(rank == 0)))
+    sdc = shared(synth.synth_controlnet_state_dict(dev, 4321, fill=(rank == 0)))
+    net, cnet = TGUNet(sdu, dev), TGControlNet(sdc, dev)
     eng = DenoiseEngine(net, controlnet=cnet)
     K, STEPS = 4, 50
     ctx1, ctx2, lat1, lat2, x0, nz, scale1 = build_inputs(torch, dev, K)
@@ -362,12 +504,26 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_device_mixed if mixed else step_device, Kb, Wb, nvtx="tg_timed")
+    # timestep index of loop iteration i: the timed region starts at index 0 of a trajectory
+    dev_fn, e2e_fn = (step_device_mixed, step_e2e_mixed) if mixed else (step_device, step_e2e)
+    ms_dev = timed(lambda i: dev_fn(i - Wb), Kb, Wb, nvtx="tg_timed")
     clocks = sampler.stop() if rank == 0 else None
-    n_energy = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) < 30)
-    n_embed = sum(1 for i in range(Wb, Wb + Kb) if (i % STEPS) == 0)
+    n_energy = sum(1 for i in range(Kb) if (i % STEPS) < 30)
+    n_embed = sum(1 for i in range(Kb) if (i % STEPS) == 0)
     gpu_launches = n_energy * launches_per_step[True] + (Kb - n_energy) * launches_per_step[False] + n_embed * embed_launches
-    ms_e2e = timed(step_e2e_mixed if mixed else step_e2e, Kb, Wb)
+    ms_e2e = timed(lambda i: e2e_fn(i - Wb), Kb, Wb)
+
+    # ---- sustained leg: >= 3 s of the same device-resident loop (DESIGN "law 5": dense work is power capped) ----
+    sustained = None
+    if not args.no_sustained:
+        n_sus = 5 * STEPS
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        ms_sus = timed(lambda i: dev_fn(i - Wb), n_sus, Wb)
+        c2 = s2.stop() if rank == 0 else None
+        sustained = {"value": round((K + 1) * world * n_sus / (ms_sus * 1e-3), 2), "unit": "steps/s", "steps": n_sus,
+                     "seconds": round(ms_sus * 1e-3, 3), "ms_per_step": round(ms_sus / n_sus, 4), "clocks": c2}
 
     # ---- replay time of each captured graph on its own (where the step time goes) ----
     def graph_ms(g, n=10):
@@ -492,6 +648,21 @@ def run_ours(args):
         except Exception as ex:  # the leg is informational; the main line must still print
             grad_leg = {"error": f"{type(ex).__name__}: {ex}"}
 
+    # ---- parity leg (checker): the co-batched graphs that were timed, 50 steps from index 0, vs the oracle loops ----
+    parity = None
+    if rank == 0 and world == 1 and mixed and not args.no_parity:
+        try:
+            parity = parity_leg(torch, dev, gme, gm, embed_hint, d_hint, d_ts, d_coef, d_frozen, h_latm, sdu, sdc,
+                                ctx1, ctx2, lat1, lat2, ctrl_ctx, mask, bboxes, K, STEPS)
+        except Exception as ex:  # informational: the main line must still print
+            parity = {"error": f"{type(ex).__name__}: {ex}"}
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_reference:
+        try:
+            eager = eager_reference_leg(torch, dev, sdu, sdc, ctx1, ctx2, lat1, lat2, ctrl_ctx, d_hint, d_frozen, mask, K)
+        except Exception as ex:
+            eager = {"error": f"{type(ex).__name__}: {ex}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         total, cores = cpu_denoise_steps(2, 1)
@@ -521,6 +692,7 @@ def run_ours(args):
                                                                 + FLOPS_CONTROLNET_STEP) / 1e12 / peaks()[0], 4),
             "roofline": roof, "cpu_baseline": cpu, "graph_replay_ms": graphs,
             "kernel_breakdown_per_forward": breakdown, "guidance_gradient": grad_leg,
+            "parity": parity, "gpu_eager_reference": eager, "sustained": sustained,
         }
         print(json.dumps(out))
     if world > 1:
@@ -534,6 +706,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 3 s sustained leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 50-step oracle parity leg (~40 s)")
+    ap.add_argument("--no-eager-reference", action="store_true", help="skip the same-GPU PyTorch eager leg")
     ap.add_argument("--separate-stage2", action="store_true", help="stage-1 (B=8) and stage-2 (B=2) as separate forwards")
     args = ap.parse_args()
     if args.impl == "reference":

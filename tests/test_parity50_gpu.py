@@ -76,8 +76,14 @@ def test_config3_four_characters_stage2_composite_energy_50_steps(world):
     ours4 = _ours_stage1(w, 4)
     s = P.summarize(ours4, w["ref32"], w["ref16"])
     _check("config 3 stage 1 (4 co-batched characters, 50 steps)", s)
-    if "ours2" in w:  # a character's trajectory does not depend on who shares its forward: bit exact over 50 steps
-        assert torch.equal(ours4[:, :2], w["ours2"])
+    if "ours2" in w:
+        # Batch POSITION never changes a result (tests/test_pipeline_gpu.py: co-batch == solo at equal batch size), but the
+        # batch SIZE selects tile widths / split-K per GEMM shape, i.e. a different fp32 summation order -- like cuBLAS
+        # heuristics do for the reference.  The two runs of the same characters must stay inside the fp16 noise floor.
+        d = (ours4[:, :2].float() - w["ours2"].float()).abs().amax(dim=(1, 2, 3, 4))
+        e16 = (w["ref16"][:, :2].float() - w["ref32"][:, :2]).abs().amax(dim=(1, 2, 3, 4))
+        print("  K=4 vs K=2 co-batch, same characters, per-step max diff:", [round(float(v), 5) for v in d[::5]])
+        assert (d <= e16 + 5e-3).all()
 
     # stage 2: ControlNet + composite on every step + capture of the guidance maps + energy for index < 30
     g = torch.Generator().manual_seed(77)
