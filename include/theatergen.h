@@ -85,6 +85,14 @@ int tg_gemm_set_scratch_slot(int slot);
  * tg_conv3x3 CTA records {main-loop cycles, producer wait, MMA wait on data, MMA wait on accumulator, epilogue wait,
  * k-blocks, tiles} so a run can tell which role of the pipeline the others wait for.  NULL switches it off. */
 int tg_gemm_set_prof(void* dev_buf);
+/* Same for tg_attention_tc: with a non-NULL device buffer of >= 8 int64 per softmax warp (4 per CTA, CTAs in grid order
+ * (x fastest)), every softmax warp records {wait for S, wait for tcgen05.ld, max (+ lazy rescale), exponentials + P store
+ * issue, store wait + arrive, tiles, SM id, end clock}.  NULL switches it off. */
+int tg_attn_set_prof(void* dev_buf);
+/* Measurement hook: schedule of tg_attention_tc's kernels -- 0 (default): P overlays S, one query tile per CTA; 2: P in its
+ * own tensor-memory columns, score tiles issued two tiles ahead; 3: two query tiles per CTA with alternating MUFU turns
+ * (d <= 56, N % 256 == 0; else as 2).  Same results within the kernel's tolerance; process-wide. */
+int tg_attn_set_variant(int v);
 
 /* Launch-geometry knobs of tg_groupnorm for measurements (values <= 0 keep the current setting; fused: 1 allows the
  * single-kernel cluster path for tensors whose per-image slab fits on chip, 0 forces the two-pass kernels, <0 keeps).

@@ -70,6 +70,37 @@ def test_self_attention_tcgen05_lazy_rescale():
     _close(out, ref, 3e-3, 1e-2, "tcgen05 self-attn (lazy rescale)")
 
 
+@pytest.mark.parametrize("variant", [2, 3])
+def test_self_attention_tcgen05_alternative_schedules(variant):
+    """tg_attn_set_variant: the measured alternatives of the softmax / MMA-issue schedule (P in its own tensor-memory
+    columns; two query tiles per CTA with alternating MUFU turns) give the default schedule's results within the
+    kernel's tolerance, lazy rescale included."""
+    from theatergen_b200 import _lib, ops
+    heads = 8
+    try:
+        for B, N, d, ramp_hi in ((2, 4096, 40, 0.0), (3, 1024, 40, 6.0), (1, 256, 16, 0.0), (2, 384, 48, 4.0), (2, 1024, 80, 0.0)):
+            pad = 64 if d + 1 <= 64 else 128
+            qkv = torch.zeros((B * N, 3, heads, pad), dtype=torch.float16, device="cuda")
+            base = _rand((B * N, 3, heads, d), 11 + N, 1.2)
+            if ramp_hi:
+                ramp = torch.linspace(0.2, ramp_hi, N, device="cuda").repeat(B)[:, None, None]
+                base[:, 1] = (base[:, 1].float() * ramp).half()
+            qkv[..., :d] = base
+            flat = qkv.view(B * N, 3 * heads * pad)
+            P = heads * pad
+            _lib.check(_lib.lib().tg_attn_set_variant(0), "tg_attn_set_variant")
+            want = ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d)
+            _lib.check(_lib.lib().tg_attn_set_variant(variant), "tg_attn_set_variant")
+            got = ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d)
+            q, k, v = [qkv[:, i, :, :d].float().reshape(B, N, heads, d).transpose(1, 2) for i in range(3)]
+            ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * N, heads * d)
+            _close(got, ref, 3e-3, 1e-2, f"tcgen05 self-attn variant {variant} N={N} d={d}")
+            assert (got.float() - want.float()).abs().max().item() < 2e-3
+            assert torch.equal(got, ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d))
+    finally:
+        _lib.lib().tg_attn_set_variant(0)
+
+
 def test_self_attention_cross_lengths():
     """Nq != Nk (the resampler: 16 queries over 273 keys) and sharper logits."""
     from theatergen_b200 import ops

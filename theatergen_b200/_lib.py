@@ -22,6 +22,8 @@ _SIGS = {
     "tg_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, ci, ci, cf, vp, ci, vp]),
     "tg_groupnorm": (ci, [vp, ci, vp, ci, ci, ci, vp, vp, cf, ci, vp, vp, vp]),
     "tg_gemm_set_prof": (ci, [vp]),
+    "tg_attn_set_prof": (ci, [vp]),
+    "tg_attn_set_variant": (ci, [ci]),
     "tg_gemm_set_scratch_slot": (ci, [ci]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),

@@ -249,7 +249,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches non-divergent and
+  // the operands of tcgen05.mma / TMA instructions in uniform registers.  With `threadIdx.x >> 5` and a lane-0 branch
+  // every tcgen05.mma was wrapped in an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY loop (21 instructions, measured in the
+  // attention kernel at ~115-170 cycles per MMA issued) -- more than the 64-128 cycles the MMA occupies the tensor pipe.
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int nk = KY3 ? g.K / (3 * BK) : g.K / BK;  // KY3: units of (kx, channel block) = three k-blocks each
   const int S = g.splits;
@@ -293,11 +297,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
   grid_dep_launch();
   grid_dep_wait();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: warp-uniform loop (all lanes wait), one elected lane issues =====
+    {
+      const bool leader = elect_one();
       int it = 0;  // k-iteration counter across work items (ring position)
       long long p_wait = 0;
       const int hw = g.H * g.W;
@@ -331,10 +336,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             uint8_t* sb = sa + L::A_STAGE_BYTES;
             const uint32_t bytes = (uint32_t)g.patch_bytes + 3 * L::B_BYTES;
             const uint32_t fb = mapa_rank(smem_u32(&full_bar[s]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
             const int kx = kb / cblk, cb = kb - kx * cblk;
-            tma_load_4d_2sm(sa, &tmA2, fb, cb * BK, kx - 1, conv_y0 - 1, conv_b0);
-            tma_load_4d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb, 0);
+            if (leader) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
+              tma_load_4d_2sm(sa, &tmA2, fb, cb * BK, kx - 1, conv_y0 - 1, conv_b0);
+              tma_load_4d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb, 0);
+            }
           }
           continue;
         }
@@ -357,10 +364,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           if (PAIR) {
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
             fb = mapa_rank(smem_u32(&full_bar[s]), 0);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
+            if (rank == 0 && leader) mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
           } else {
-            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            if (leader) mbar_arrive_expect_tx(&full_bar[s], bytes);
           }
+          if (leader)
           for (int j = 0; j < nkb; ++j) {
             uint8_t* dst = sa + j * L::A_BYTES;
             if (g.mode == 0) {
@@ -376,15 +384,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               else tma_load_4d(dst, &tmA1, &full_bar[s], c0, conv_x0 + kx - 1, conv_y0 + ky - 1, conv_b0);
             }
           }
-          if (PAIR) tma_load_3d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb);  // my half of the weight tile
-          else tma_load_3d(sb, &tmB, &full_bar[s], 0, n0, kb);
+          if (leader) {
+            if (PAIR) tma_load_3d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb);  // my half of the weight tile
+            else tma_load_3d(sb, &tmB, &full_bar[s], 0, n0, kb);
+          }
         }
       }
-      if (g.prof) g.prof[blockIdx.x * 8 + 1] = p_wait;
+      if (g.prof && leader) g.prof[blockIdx.x * 8 + 1] = p_wait;
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0 && rank == 0) {
+    // ===== MMA issuer: the whole warp walks the loop (waits included) so every address stays warp-uniform; one elected
+    // lane issues the MMAs and commits =====
+    if (rank == 0) {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN);
       int it = 0, j = 0;
       long long m_wait_full = 0, m_wait_acc = 0;
@@ -414,19 +426,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             tc_fence_after();
             const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
             const uint32_t b_base = a_base + L::A_STAGE_BYTES;
+            if (leader) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const uint32_t a_addr = a_base + ky * g.ky_stride, b_addr = b_base + ky * L::B_BYTES;
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint32_t a_addr = a_base + ky * g.ky_stride, b_addr = b_base + ky * L::B_BYTES;
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
-                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
-                umma_f16_ss_2sm(d_addr, da, db, idesc, (kb > kb0 || ky > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
+                  const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
+                  umma_f16_ss_2sm(d_addr, da, db, idesc, (kb > kb0 || ky > 0 || k > 0) ? 1u : 0u);
+                }
               }
+              tc_commit_2sm(&empty_bar[s], 0x3);
             }
-            tc_commit_2sm(&empty_bar[s], 0x3);
           }
-          tc_commit_2sm(&acc_full[as], 0x3);
+          if (leader) tc_commit_2sm(&acc_full[as], 0x3);
           continue;
         }
         for (int kb = kb0; kb < kb1; kb += KPS, ++it) {
@@ -443,30 +457,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const int nkb = (kb1 - kb) < KPS ? (kb1 - kb) : KPS;
           const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
           const uint32_t b_base = a_base + KPS * L::A_BYTES;
-          for (int j = 0; j < nkb; ++j) {
-            const uint32_t a_addr = a_base + j * L::A_BYTES, b_addr = b_base + j * L::B_BYTES;
+          if (leader) {
+            for (int j = 0; j < nkb; ++j) {
+              const uint32_t a_addr = a_base + j * L::A_BYTES, b_addr = b_base + j * L::B_BYTES;
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
-              const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
-              const uint32_t acc = (kb + j > kb0 || k > 0) ? 1u : 0u;
-              if (PAIR)
-                umma_f16_ss_2sm(d_addr, da, db, idesc, acc);
-              else
-                umma_f16_ss(d_addr, da, db, idesc, acc);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32);
+                const uint64_t db = make_smem_desc_sw128(b_addr + k * 32);
+                const uint32_t acc = (kb + j > kb0 || k > 0) ? 1u : 0u;
+                if (PAIR)
+                  umma_f16_ss_2sm(d_addr, da, db, idesc, acc);
+                else
+                  umma_f16_ss(d_addr, da, db, idesc, acc);
+              }
             }
+            if (PAIR)
+              tc_commit_2sm(&empty_bar[s], 0x3);  // frees the stage in both CTAs when these MMAs retire
+            else
+              tc_commit(&empty_bar[s]);
           }
-          if (PAIR)
-            tc_commit_2sm(&empty_bar[s], 0x3);  // frees the stage in both CTAs when these MMAs retire
-          else
-            tc_commit(&empty_bar[s]);
         }
-        if (PAIR)
-          tc_commit_2sm(&acc_full[as], 0x3);  // accumulator halves complete in both CTAs
-        else
-          tc_commit(&acc_full[as]);
+        if (leader) {
+          if (PAIR)
+            tc_commit_2sm(&acc_full[as], 0x3);  // accumulator halves complete in both CTAs
+          else
+            tc_commit(&acc_full[as]);
+        }
       }
-      if (g.prof) {
+      if (g.prof && leader) {
         g.prof[blockIdx.x * 8 + 0] = clock64() - m_t0;
         g.prof[blockIdx.x * 8 + 2] = m_wait_full;
         g.prof[blockIdx.x * 8 + 3] = m_wait_acc;

@@ -31,6 +31,8 @@ int gemm_set_scratch_slot(int slot);
 // measurement hook: when non-null every GEMM CTA writes 8 counters {main-loop cycles, producer wait, MMA wait(full),
 // MMA wait(accumulator), epilogue wait, k-blocks, tiles, -} at dev_buf[blockIdx.x*8..] (tools/gemm_probe.py)
 void gemm_set_prof(long long* dev_buf);
+void attn_set_prof(long long* dev_buf);
+void attn_set_variant(int v);
 
 // GroupNorm(32 groups)(+SiLU) over the channel-concat [x1 | x2] (x2 may be null, C2 = 0); fp32 statistics.
 // workspace: >= B*64*32*2 floats.

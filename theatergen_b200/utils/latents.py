@@ -93,3 +93,24 @@ def compose_latents(adapter, model_dict, latents_all_list, mask_tensor_list, num
         me = m[None, None, None].to(dtype)
         composed = composed * (1. - me) + latents_all_list[i][:n].to(dev) * me
     return composed, fg_idx
+
+
+@torch.no_grad()
+def compose_latents_with_alignment(basever, adapter, repeat_ind, mask_tensor_list_512, single_obj_img_list, model_dict,
+                                   latents_all_list, mask_tensor_list, num_inference_steps, overall_batch_size, height,
+                                   width, align_with_overall_bboxes=True, overall_bboxes=None,
+                                   horizontal_shift_only=False, prepare_mid_image=None, **kwargs):
+    """utils/latents.py:242-255.  The PIL collage + inpainting mask of `prepare_mid_image` (latents.py:48-135) is image
+    munging outside the hot path: pass the reference's function as `prepare_mid_image` to get (inp_mask, inp_img);
+    without it both are None."""
+    inp_mask = inp_img = None
+    if align_with_overall_bboxes and len(latents_all_list):
+        expanded = utils.expand_overall_bboxes(overall_bboxes)
+        latents_all_list, mask_tensor_list, _ = align_with_bboxes(latents_all_list, mask_tensor_list, bboxes=expanded,
+                                                                  horizontal_shift_only=horizontal_shift_only)
+        if prepare_mid_image is not None:
+            inp_mask, inp_img = prepare_mid_image(basever, repeat_ind, mask_tensor_list_512, single_obj_img_list,
+                                                  bboxes=expanded)
+    composed, fg_idx = compose_latents(adapter, model_dict, latents_all_list, mask_tensor_list, num_inference_steps,
+                                       overall_batch_size, height, width, **kwargs)
+    return composed, fg_idx, inp_mask, inp_img

@@ -1,0 +1,114 @@
+// Pipe costs the attention softmax is built on: cycles per warp-instruction of MUFU.EX2, F2FP.F16.F32.PACK_AB, FFMA,
+// FFMA2 (fma.rn.f32x2) and a degree-3 polynomial exp2 on the FMA/ALU pipes, for one warp per scheduler and for two.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o xu_probe xu_probe.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_fp16.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exp2 on the FMA / ALU pipes: round-to-nearest split + degree-3 polynomial + exponent insertion
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -30.f);
+  const float xf = x + 12582912.f;
+  const float n = xf - 12582912.f;
+  const float f = x - n;
+  float p = 0.0555041f;
+  p = fmaf(p, f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xf) << 23));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) probe(int iters, float seed, long long* out, float* sink) {
+  float x[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) x[i] = seed * (i + threadIdx.x) * 1e-3f - 3.f;
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {  // 64 MUFU.EX2
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] = ex2(x[i]) - 1.5f;
+    } else if (MODE == 1) {  // 64 MUFU.EX2 + 32 F2FP
+      float y[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) y[i] = ex2(x[i]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const __half2 h = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+        acc ^= *reinterpret_cast<const uint32_t*>(&h);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] += 0.001f;
+    } else if (MODE == 2) {  // 32 F2FP only (+64 FADD)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+        acc ^= *reinterpret_cast<const uint32_t*>(&h);
+      }
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] += 0.001f;
+    } else if (MODE == 3) {  // 64 FADD only (baseline of modes 1, 2)
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] += 0.001f;
+    } else if (MODE == 4) {  // 64 polynomial exp2
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] = ex2_poly(x[i]) - 1.5f;
+    } else if (MODE == 5) {  // 48 MUFU + 16 polynomial, interleaved
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] = ((i & 3) == 3 ? ex2_poly(x[i]) : ex2(x[i])) - 1.5f;
+    } else if (MODE == 6) {  // 32 MUFU + 32 polynomial
+#pragma unroll
+      for (int i = 0; i < 64; ++i) x[i] = ((i & 1) ? ex2_poly(x[i]) : ex2(x[i])) - 1.5f;
+    } else if (MODE == 7) {  // 64 FFMA2 (fma.rn.f32x2): 128 fp32 FMAs
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        unsigned long long v, a = 0x3f8000003f800000ull, b = 0x3a83126f3a83126full;
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(x[i]), "f"(x[i + 1]));
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(a), "l"(b));
+        asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(a), "l"(b));
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x[i]), "=f"(x[i + 1]) : "l"(v));
+      }
+    } else if (MODE == 8) {  // 128 FFMA
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { x[i] = fmaf(x[i], 1.0001f, 0.001f); x[i] = fmaf(x[i], 1.0001f, 0.001f); }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s += x[i];
+  if (s == 12345.f || acc == 0x1234567u) sink[0] = s + acc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+template <int MODE>
+static void run(const char* name, long long* d_out, float* d_sink) {
+  for (int threads : {128, 256}) {
+    probe<MODE><<<148, threads>>>(2000, 1.0f, d_out, d_sink);
+    probe<MODE><<<148, threads>>>(2000, 1.0f, d_out, d_sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h;
+    cudaMemcpy(&h, d_out, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s %d warp(s)/scheduler: %7.1f cycles per iteration  %s\n", name, threads / 128, h / 2000.0,
+           e == cudaSuccess ? "" : cudaGetErrorString(e));
+  }
+}
+
+int main() {
+  long long* d_out; float* d_sink;
+  cudaMalloc(&d_out, 64); cudaMalloc(&d_sink, 64);
+  run<0>("64 MUFU.EX2 (+64 FADD)", d_out, d_sink);
+  run<1>("64 MUFU.EX2 + 32 F2FP.PACK (+64 FADD, 32 LOP)", d_out, d_sink);
+  run<2>("32 F2FP.PACK (+64 FADD, 32 LOP)", d_out, d_sink);
+  run<3>("64 FADD", d_out, d_sink);
+  run<4>("64 polynomial exp2 (+64 FADD)", d_out, d_sink);
+  run<5>("48 MUFU.EX2 + 16 polynomial (+64 FADD)", d_out, d_sink);
+  run<6>("32 MUFU.EX2 + 32 polynomial (+64 FADD)", d_out, d_sink);
+  run<7>("64 FFMA2 (= 128 fp32 FMA) + pack/unpack movs", d_out, d_sink);
+  run<8>("128 FFMA", d_out, d_sink);
+  return 0;
+}
