@@ -42,6 +42,7 @@ class StepGraph:
         self.engine = engine
         self.graph = None
         self.launches_per_step = 0
+        self.replays = 0
 
     def _control(self, r0, r1):
         if not self.use_controlnet:
@@ -75,6 +76,7 @@ class StepGraph:
 
     def replay(self):
         self.graph.replay()
+        self.replays += 1
 
 
 class MixedStepGraph(StepGraph):
@@ -126,6 +128,10 @@ class DenoiseEngine:
         self.use_graphs = use_graphs
         self._graphs = {}
         self._tables = {}
+
+    def launches_replayed(self):
+        """kernels launched through graph replays so far (tg_launch_count only sees eager launches and captures)"""
+        return sum(g.launches_per_step * g.replays for g in self._graphs.values())
 
     def tables(self, num_steps, guidance_scale):
         key = (num_steps, float(guidance_scale))
