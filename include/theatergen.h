@@ -93,6 +93,9 @@ int tg_attn_set_prof(void* dev_buf);
  * own tensor-memory columns, score tiles issued two tiles ahead; 3: two query tiles per CTA with alternating MUFU turns
  * (d <= 56, N % 256 == 0; else as 2).  Same results within the kernel's tolerance; process-wide. */
 int tg_attn_set_variant(int v);
+/* Measurement hook: implementation behind tg_attention_cross_ip -- -1 (default) the tcgen05 / TMEM kernel for head dims
+ * <= 64 and the mma.sync kernel above (each where it measured faster), 0 mma.sync everywhere, 1 tcgen05 everywhere. */
+int tg_attn_cross_set_impl(int mode);
 
 /* Launch-geometry knobs of tg_groupnorm for measurements (values <= 0 keep the current setting; fused: 1 allows the
  * single-kernel cluster path for tensors whose per-image slab fits on chip, 0 forces the two-pass kernels, <0 keeps).

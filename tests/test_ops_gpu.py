@@ -114,9 +114,19 @@ def test_self_attention_cross_lengths():
     _close(out, ref, 2e-3, 1e-2, "cross-length attn")
 
 
+@pytest.fixture(params=[-1, 0, 1], ids=["auto", "mma_sync", "tcgen05"])
+def cross_impl(request):
+    """tg_attn_cross_set_impl: every cross-attention test runs on the default dispatch, on the mma.sync kernel alone and on
+    the tcgen05 / TMEM kernel alone (all head dims)."""
+    from theatergen_b200 import _lib
+    _lib.check(_lib.lib().tg_attn_cross_set_impl(request.param), "tg_attn_cross_set_impl")
+    yield request.param
+    _lib.lib().tg_attn_cross_set_impl(-1)
+
+
 @pytest.mark.parametrize("B,N,C,n_ip", [(2, 4096, 320, 4), (2, 1024, 640, 4), (4, 256, 1280, 4), (2, 64, 1280, 16),
-                                        (2, 256, 1280, 0)])
-def test_cross_attention_ip(B, N, C, n_ip):
+                                        (2, 256, 1280, 0), (2, 200, 320, 16), (1, 64, 640, 4)])
+def test_cross_attention_ip(B, N, C, n_ip, cross_impl):
     from theatergen_b200 import ops
     heads, n_text = 8, 77
     d = C // heads
@@ -140,6 +150,17 @@ def test_cross_attention_ip(B, N, C, n_ip):
     ref = ref.transpose(1, 2).reshape(B * N, C)
     _close(out, ref, 3e-3, 1e-2, "cross-attn")
     _close(probs, p[B // 2:], 1e-3, 1e-2, "captured probs")
+    # additive attention mask (attention_processor.py:202-208 baddbmm with beta = 1): masked text tokens get -inf-like bias
+    mask = torch.zeros((B, n_text), dtype=torch.float16, device="cuda")
+    mask[:, 50:] = -10000.0
+    mask[0, 3] = -2.5
+    out_m = ops.attention_cross_ip(q, kv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:3 * C] if n_ip else None,
+                                   kv[:, 3 * C:] if n_ip else None, B, heads, n_text, n_ip, ip_scale=scale, add_mask=mask)
+    pm = torch.softmax(qq @ kt.transpose(-1, -2) * d ** -0.5 + mask.float().view(B, 1, 1, n_text), -1)
+    refm = pm @ vt
+    if n_ip:
+        refm = refm + scale.view(B, 1, 1, 1) * (pi @ vi)
+    _close(out_m, refm.transpose(1, 2).reshape(B * N, C), 3e-3, 1e-2, "cross-attn + mask")
 
 
 @pytest.mark.parametrize("B,HW,C1,C2,silu", [(2, 4096, 320, 0, True), (2, 4096, 640, 320, True),
@@ -283,8 +304,8 @@ def test_cfg_ddim_composite():
 
 
 @pytest.mark.parametrize("B,N,C", [(10, 4096, 320), (8, 4096, 320), (10, 1024, 640), (3, 1000, 320)])
-def test_cross_attention_query_tile_walk_is_batch_independent(B, N, C):
-    """A CTA of attn_cross_ip_kernel walks 1, 2 or 4 query tiles depending on the launch size (K/V staged once per CTA).
+def test_cross_attention_query_tile_walk_is_batch_independent(B, N, C, cross_impl):
+    """A CTA of the cross-attention kernels (attn_cross_ip_kernel / attn_cross_tc_kernel) walks 1, 2, 4 or 8 query tiles depending on the launch size (K/V staged once per CTA).
     Every image of a large batch must come out bit-identical to the same image run alone (one tile per CTA), captured
     probabilities included; N = 1000 leaves a ragged last tile."""
     from theatergen_b200 import ops

@@ -24,6 +24,7 @@ _SIGS = {
     "tg_gemm_set_prof": (ci, [vp]),
     "tg_attn_set_prof": (ci, [vp]),
     "tg_attn_set_variant": (ci, [ci]),
+    "tg_attn_cross_set_impl": (ci, [ci]),
     "tg_gemm_set_scratch_slot": (ci, [ci]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),

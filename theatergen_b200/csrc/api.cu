@@ -45,6 +45,11 @@ int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, in
 
 int tg_gemm_set_scratch_slot(int slot) { return tg::gemm_set_scratch_slot(slot); }
 
+int tg_attn_cross_set_impl(int mode) {
+  TG_CHECK(mode >= -1 && mode <= 1, "tg_attn_cross_set_impl: %d (-1 auto, 0 mma.sync, 1 tcgen05)", mode);
+  tg::attn_cross_set_impl(mode);
+  return 0;
+}
 int tg_attn_set_variant(int v) {
   TG_CHECK(v == 0 || v == 2 || v == 3, "tg_attn_set_variant: %d (0, 2 or 3)", v);
   tg::attn_set_variant(v);

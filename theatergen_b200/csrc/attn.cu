@@ -486,10 +486,24 @@ static int launch_cross(const __half* Q, int ldq, const __half* Kt, const __half
   return 0;
 }
 
+static int g_cross_impl = -2;  // -2: not read from the environment yet
+void attn_cross_set_impl(int mode) { g_cross_impl = mode; }
+
 int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
                        const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
                        const __half* add_mask, __half* O, int ldo, __half* probs, int probs_b0, int B, int heads,
                        int Nq, int d, float scale, cudaStream_t st) {
+  // Two implementations with the same results (tests/test_ops_gpu.py runs both on every shape):
+  //   attn_cross_tc.cu  tcgen05 / TMEM: one 96-key tile, TS-form MMAs -- used for head dims <= 64 (the 64x64 level, 78 %
+  //                     of the cross-attention bytes), where it matches the mma.sync kernel (38.4 vs 38.9 us at B = 10)
+  //   this file         mma.sync, several small CTAs per SM -- still faster for d = 80 / 160 (20.7 vs 31.0 us, 15.6 vs
+  //                     23.2 us): one 128-query tile per tensor-memory allocation is a strictly sequential
+  //                     Q -> S -> softmax -> P -> O chain and 512 columns do not hold two of them at these head dims
+  // tg_attn_cross_set_impl / TG_CROSS_TC: -1 auto (default), 0 mma.sync everywhere, 1 tcgen05 everywhere.
+  if (g_cross_impl == -2) g_cross_impl = getenv("TG_CROSS_TC") ? atoi(getenv("TG_CROSS_TC")) : -1;
+  if (g_cross_impl == 1 || (g_cross_impl == -1 && d <= 64))
+    return attention_cross_ip_tc(Q, ldq, Kt, Vt, Ki, Vi, ldkv, n_text, n_ip, ip_scale, add_mask, O, ldo, probs, probs_b0, B, heads,
+                                 Nq, d, scale, st);
   TG_CHECK(n_text >= 1 && n_text <= XT && n_ip >= 0 && n_ip <= XI, "cross attention: n_text=%d (<=80) n_ip=%d (<=16)",
            n_text, n_ip);
   TG_CHECK(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 2 == 0, "cross attention: pitches must be 16B aligned");

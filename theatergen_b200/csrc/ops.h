@@ -33,6 +33,7 @@ int gemm_set_scratch_slot(int slot);
 void gemm_set_prof(long long* dev_buf);
 void attn_set_prof(long long* dev_buf);
 void attn_set_variant(int v);
+void attn_cross_set_impl(int mode);
 
 // GroupNorm(32 groups)(+SiLU) over the channel-concat [x1 | x2] (x2 may be null, C2 = 0); fp32 statistics.
 // workspace: >= B*64*32*2 floats.
@@ -51,6 +52,10 @@ int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int
                  int B, int heads, int N, int d, float scale, cudaStream_t st);
 // text + image-token cross attention (see attn.cu)
 int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
+                       const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
+                       const __half* add_mask, __half* O, int ldo, __half* probs, int probs_b0, int B, int heads,
+                       int Nq, int d, float scale, cudaStream_t st);
+int attention_cross_ip_tc(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
                        const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,
                        const __half* add_mask, __half* O, int ldo, __half* probs, int probs_b0, int B, int heads,
                        int Nq, int d, float scale, cudaStream_t st);
