@@ -601,10 +601,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         mbar_wait(&acc_full[as], (j >> 1) & 1);
       }
       tc_fence_after();
-      // accumulator chunks are read one ahead: the tcgen05.ld of chunk i+1 (~80 cycles) travels while chunk i goes through
-      // bias / activation / residual / rounding / staging (the short-K linears are paced by this epilogue)
-      uint32_t r_next[32];
-      if (g.act != 2 && c_first < BN) tmem_ld_32x32b_x32(lane_addr + c_first, r_next);
 #pragma unroll 1
       for (int c = c_first; c < BN; c += 2 * step, ++chunk_ctr) {
         uint8_t* buf = my_stage + (chunk_ctr & 1) * (EPI_BUF_BYTES / 2);
@@ -616,10 +612,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (c_nxt < BN) load_residual(g, res_next, m, g.act == 2 ? (n0 + c_nxt) >> 1 : n0 + c_nxt, row_ok);
         float v[EC];
         if (g.act != 2) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(lane_addr + c, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r_next[i]);
-          if (c_nxt < BN) tmem_ld_32x32b_x32(lane_addr + c_nxt, r_next);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
         } else {
           // GEGLU: accumulator columns packed per 64 as [32 value | 32 gate]; bias packed the same way
           // (ip_adapter/attention.py:359-367).  value * gelu_erf(gate) is formed in fp32 and rounded once.
