@@ -66,6 +66,20 @@ int tg_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt
                const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, int act, float out_scale,
                tg_half* out, int ldc, void* stream);
 
+/* out[B*(H/2)*(W/2), Cout] = act(conv3x3(stride 2)(X[B,H,W,Cin]) + bias): diffusers Downsample2D (call sites
+ * ip_adapter/unet_2d_blocks.py:1035,1112,1161,1198; the ControlNet's conditioning embedder and encoder; pad_lo = 0: the VAE
+ * encoder's one-sided padding).  Implicit GEMM: the TMA gathers every other pixel (element stride 2), no im2col buffer.
+ * Wt = [Cout,3,3,Cin]; H, W even; the output width must divide 128 or be a multiple of it. */
+int tg_conv3x3_s2(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt, int Cout, const tg_half* bias, int pad_lo,
+                  int act, tg_half* out, int ldc, void* stream);
+
+/* out[B,2H,2W,Cout] = conv3x3(pad 1)(nearest_x2(X[B,H,W,Cin])) + bias: diffusers Upsample2D (ip_adapter/unet_2d_blocks.py:
+ * 2184,2251,2298,2332) without the upsampled tensor: four 2x2 convolutions on the low-resolution grid, one per output
+ * pixel parity (py, px), 2.25x fewer multiply-adds.  Wt4 = [4][Cout,2,2,Cin]: for phase p = 2 py + px, tap (a, b) is the sum
+ * of the 3x3 taps (ky, kx) that read input row i + py - 1 + a and column j + px - 1 + b. */
+int tg_upsample2x_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const tg_half* Wt4, int Cout, const tg_half* bias,
+                          tg_half* out, void* stream);
+
 /* out = [SiLU](GroupNorm32([x1|x2])) for channels-last x1 [B,HW,C1], x2 [B,HW,C2] (x2 NULL when C2 == 0).
  * The up-path torch.cat([hidden, skip], 1) (ip_adapter/unet_2d_blocks.py:2210-2212, 2318-2320) is folded in.
  * workspace: >= 16640 + B*16384 floats, ZERO-INITIALISED once (holds self-resetting arrival counters); B <= 256.

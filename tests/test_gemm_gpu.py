@@ -1,6 +1,7 @@
 """GPU parity of the tcgen05 GEMM / implicit-GEMM conv against an fp32 torch reference of the same op."""
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -171,3 +172,49 @@ def test_conv3x3_patch_reuse_tiles(B, H, W, Cin, Cout):
         assert torch.equal(ops.conv3x3(x, w, bias, residual=res), outs[(128, 1, 1)])
     finally:
         L.tg_gemm_force_tile(0, 1, 0)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,pad_lo", [(2, 64, 320, 320, 1), (10, 32, 640, 640, 1), (2, 16, 1280, 1280, 1),
+                                                 (1, 512, 64, 64, 1), (1, 256, 128, 128, 0), (3, 32, 64, 192, 0)])
+def test_conv3x3_stride2_implicit_gemm(B, H, Cin, Cout, pad_lo):
+    """Downsample2D (ip_adapter/unet_2d_blocks.py:1035,1112,1161,1198): stride-2 3x3 convolution whose operand is gathered by
+    the TMA with an element stride of 2 -- against F.conv2d and against the im2col + GEMM path of round 1 (bit exact: same
+    products, same accumulation order per output)."""
+    from theatergen_b200 import ops
+    x = _rand((B, H, H, Cin), 1)
+    w = _rand((Cout, Cin, 3, 3), 2, (9 * Cin) ** -0.5)
+    bias = _rand((Cout,), 3, 0.1)
+    wp = w.permute(0, 2, 3, 1).contiguous()
+    out = ops.conv3x3_s2(x, wp, bias, pad_lo=pad_lo)
+    xin = x.float().permute(0, 3, 1, 2)
+    if pad_lo == 0:
+        xin = F.pad(xin, (0, 1, 0, 1))
+    ref = F.conv2d(xin, w.float(), bias.float(), stride=2, padding=1 if pad_lo else 0).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _close(out, ref, 3e-3, 3e-3)
+    old = ops.gemm(ops.im2col_s2(x, pad_lo=pad_lo), wp.reshape(Cout, 9 * Cin), bias).view(B, H // 2, H // 2, Cout)
+    assert (out.float() - old.float()).abs().max().item() < 2e-3
+    y = ops.conv3x3_s2(x, wp, bias, pad_lo=pad_lo, act=ops.TG_ACT_SILU)
+    _close(y, F.silu(ref), 3e-3, 3e-3)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 8, 1280, 1280), (10, 16, 1280, 1280), (2, 32, 640, 640), (1, 64, 512, 512),
+                                          (1, 128, 256, 256), (1, 256, 64, 128)])
+def test_upsample2x_conv3x3_four_phases(B, H, Cin, Cout):
+    """Upsample2D (ip_adapter/unet_2d_blocks.py:2184,2251,2298,2332): nearest x2 + 3x3 convolution computed as four 2x2
+    convolutions on the low-resolution grid (weights.pack_upsample_conv3x3), each phase stored through a 3D tensor map into
+    its pixels of the [B,2H,2W,C] image -- against F.interpolate + F.conv2d in fp32 and against the materialising path."""
+    from theatergen_b200 import ops
+    from theatergen_b200.weights import pack_upsample_conv3x3
+    x = _rand((B, H, H, Cin), 1)
+    w = _rand((Cout, Cin, 3, 3), 2, (9 * Cin) ** -0.5)
+    bias = _rand((Cout,), 3, 0.1)
+    w4 = pack_upsample_conv3x3(w)
+    assert w4.shape == (4, Cout, 2, 2, Cin)
+    out = ops.upsample2x_conv3x3(x, w4, bias)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias.float(), padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _close(out, ref, 3e-3, 3e-3)
+    old = ops.conv3x3(ops.upsample2x(x), w.permute(0, 2, 3, 1).contiguous(), bias)
+    assert (out.float() - old.float()).abs().max().item() < 4e-3

@@ -25,6 +25,8 @@ _SIGS = {
     "tg_attn_set_prof": (ci, [vp]),
     "tg_attn_set_variant": (ci, [ci]),
     "tg_attn_cross_set_impl": (ci, [ci]),
+    "tg_conv3x3_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp]),
+    "tg_upsample2x_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, vp]),
     "tg_gemm_set_scratch_slot": (ci, [ci]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),

@@ -19,7 +19,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .unet import BLOCK_OUT, _BlockNet, _getter, pack_resnet, pack_transformer
+from .unet import BLOCK_OUT, _BlockNet, _getter, downsample_conv, pack_resnet, pack_transformer
 from .weights import pack_conv3x3
 
 COND_CHANNELS = (16, 32, 96, 256)
@@ -127,7 +127,7 @@ class TGControlNet(_BlockNet):
                 h = ops.conv3x3(h, wt, bs, act=ops.TG_ACT_SILU)
             else:
                 H, W = H // 2, W // 2
-                h = ops.gemm(ops.im2col_s2(h), wt, bs, act=ops.TG_ACT_SILU).view(n, H, W, cout)
+                h = downsample_conv(h, wt, bs, cout, act=ops.TG_ACT_SILU)
         return ops.conv3x3(h, w["ce.out.w"], w["ce.out.b"])
 
     def encode(self, sample, t_dev, ctx, cond_emb):

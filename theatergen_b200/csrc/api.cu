@@ -36,6 +36,24 @@ int tg_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* W
   return tg::conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, e, HM(out), ldc, ST(stream));
 }
 
+int tg_conv3x3_s2(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* Wt, int Cout, const tg_half* bias, int pad_lo,
+                  int act, tg_half* out, int ldc, void* stream) {
+  TG_CHECK(X && Wt && out, "tg_conv3x3_s2: null pointer");
+  TG_CHECK(pad_lo == 0 || pad_lo == 1, "tg_conv3x3_s2: pad_lo must be 0 or 1");
+  TG_CHECK(act == 0 || act == 1, "tg_conv3x3_s2: act must be none / silu");
+  tg::EpilogueSpec e;
+  e.bias = H(bias); e.act = act;
+  return tg::conv3x3_s2_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, pad_lo, e, HM(out), ldc, ST(stream));
+}
+
+int tg_upsample2x_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* Wt4, int Cout, const tg_half* bias,
+                          tg_half* out, void* stream) {
+  TG_CHECK(X && Wt4 && out, "tg_upsample2x_conv3x3: null pointer");
+  tg::EpilogueSpec e;
+  e.bias = H(bias);
+  return tg::upsample2x_conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt4), Cout, e, HM(out), ST(stream));
+}
+
 
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream) {

@@ -326,6 +326,8 @@ int make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_w_ky3(CUtensorMap* out, const void* base, uint64_t rows, uint64_t Cin, uint32_t box_rows);
 // 4D NHWC fp16 [B, H, W, C]; box = [bb, bh, bw, 64], SWIZZLE_128B, OOB zero fill (conv padding)
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
-                   uint32_t bh, uint32_t bw);
+                   uint32_t bh, uint32_t bw, uint32_t pixel_stride = 1);
+int make_tmap_phase_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t W, uint64_t C, uint32_t box_w,
+                        uint32_t box_r);
 
 }  // namespace tg

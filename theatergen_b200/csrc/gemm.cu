@@ -49,8 +49,13 @@ static constexpr int SPLITK_MAX_TILES = 4096;
 
 struct GemmArgs {
   int M, N, K, K1;
-  int mode;  // 0 linear, 1 conv3x3
-  int H, W, Cin, box_h, box_b;
+  int mode;  // 0 linear, 1 convolution (implicit GEMM over a taps_w x taps_w window of the NHWC input)
+  int H, W, Cin, box_h, box_b;  // H, W: OUTPUT image (= the M decomposition); the input map may gather with pixel stride 2
+  // convolution geometry: tap (ky, kx) of output pixel (y, x) reads input pixel (y * in_stride + ky + off_y,
+  // x * in_stride + kx + off_x).  3x3 pad 1: taps_w 3, off -1, stride 1.  Stride-2 3x3 (Downsample2D): in_stride 2.
+  // Phase (py, px) of nearest-x2 + 3x3 on the low-resolution grid: taps_w 2, off (py - 1, px - 1).
+  int taps_w, off_y, off_x, in_stride;
+  int out3d_w;  // > 0: the output is a phase image of width out3d_w stored through a 3D map (make_tmap_phase_out)
   const __half* bias;
   const __half* rowbias;
   int rows_per_image, rowbias_ld;
@@ -90,6 +95,18 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 32 staged rows x 32 columns -> global: rows [m, m + 32) of the [M, N] output, or -- phase image of an upsampling
+// convolution -- 32 consecutive phase pixels (j fastest, then the image row) through the 3D map
+__device__ __forceinline__ void store_chunk(const CUtensorMap* m, const void* smem_src, int n, int row, int out3d_w) {
+  if (out3d_w > 0) tma_store_3d(m, smem_src, n, row % out3d_w, row / out3d_w);
+  else tma_store_2d(m, smem_src, n, row);
 }
 // ---- CTA-pair (cta_group::2) flavours ----
 // shared::cluster address of the same shared-memory location in the cluster's CTA `rank`
@@ -379,9 +396,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             } else {
               const int tap = (kb + j) / cblk;
               const int c0 = (kb + j - tap * cblk) * BK;
-              const int ky = tap / 3, kx = tap - ky * 3;
-              if (PAIR) tma_load_4d_2sm(dst, &tmA1, fb, c0, conv_x0 + kx - 1, conv_y0 + ky - 1, conv_b0);
-              else tma_load_4d(dst, &tmA1, &full_bar[s], c0, conv_x0 + kx - 1, conv_y0 + ky - 1, conv_b0);
+              const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+              const int ix = conv_x0 * g.in_stride + kx + g.off_x, iy = conv_y0 * g.in_stride + ky + g.off_y;
+              if (PAIR) tma_load_4d_2sm(dst, &tmA1, fb, c0, ix, iy, conv_b0);
+              else tma_load_4d(dst, &tmA1, &full_bar[s], c0, ix, iy, conv_b0);
             }
           }
           if (leader) {
@@ -582,7 +600,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmC, buf, n0 + c, m0 + q * 32);
+            store_chunk(&tmC, buf, n0 + c, m0 + q * 32, g.out3d_w);
             bulk_commit();
           }
         }
@@ -648,7 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmC, buf, n_out, m0 + q * 32);  // rows >= M are clipped by the tensor map
+          store_chunk(&tmC, buf, n_out, m0 + q * 32, g.out3d_w);  // rows >= M are clipped by the tensor map
           bulk_commit();
         }
       }
@@ -878,7 +896,14 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   // KY3 stages for pair-tiled convolutions whose tile lies inside one image (conv3x3_nhwc prepared the patch map as a2)
   const bool ky3 = pair && g.patch_bytes > 0 && bn <= KY3_MAX_BN && splits <= g.K / (3 * BK);
   CUtensorMap c;  // epilogue chunks: 32 rows x 32 columns (64-byte rows, 64B swizzle)
-  if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) return -1;
+  if (g.out3d_w > 0) {
+    const uint32_t bw = g.out3d_w < 32 ? g.out3d_w : 32;
+    TG_CHECK(32 % bw == 0 && g.out3d_w % bw == 0 && g.M % g.out3d_w == 0 && ldc == n_out, "phase output: W=%d M=%d ldc=%d", g.out3d_w,
+             g.M, ldc);
+    if (make_tmap_phase_out(&c, out, g.M / g.out3d_w, g.out3d_w, n_out, bw, 32 / bw)) return -1;
+  } else if (make_tmap_2d(&c, out, g.M, n_out, ldc, 32, 32)) {
+    return -1;
+  }
   g.num_m = (g.M + BM - 1) / BM;
   g.num_n = g.N / bn;
   g.splits = splits;
@@ -955,6 +980,7 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
   GemmArgs g{};
   g.M = B * H * W; g.N = Cout; g.K = 9 * Cin; g.K1 = g.K; g.mode = 1;
   g.H = H; g.W = W; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
+  g.taps_w = 3; g.off_y = g.off_x = -1; g.in_stride = 1;
   fill_args(g, e);
   CUtensorMap a1, a2;
   if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, box_w)) return -1;
@@ -967,6 +993,70 @@ int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt
     g.ky_stride = W * 128;
   }
   return dispatch(a1, a2, g, Wt, out, ldc, st);
+}
+
+// tile geometry of an implicit-GEMM convolution whose OUTPUT image is Ho x Wo: a 128-row tile = box_b images x box_h rows
+// x box_w pixels
+static int conv_boxes(int B, int Ho, int Wo, int* box_b, int* box_h, int* box_w) {
+  TG_CHECK((Wo <= 128 && 128 % Wo == 0) || Wo % 128 == 0, "conv: output width must divide 128 or be a multiple of it (got %d)", Wo);
+  *box_w = Wo < 128 ? Wo : 128;
+  *box_h = 128 / *box_w;
+  *box_b = 1;
+  if (*box_h > Ho) {
+    *box_b = *box_h / Ho;
+    *box_h = Ho;
+  }
+  TG_CHECK(Ho % *box_h == 0 && B % *box_b == 0 && *box_b * *box_h * *box_w == 128, "conv: tile %dx%dx%d does not cover 128",
+           *box_b, *box_h, *box_w);
+  return 0;
+}
+
+// 3x3 convolution with stride 2 (diffusers Downsample2D): the TMA gathers every other input pixel (traversal stride 2 on the
+// x / y dimensions of the NHWC map), so the operand never exists as an im2col buffer.  pad_lo = 1: padding 1 (UNet /
+// ControlNet); pad_lo = 0: the VAE encoder's one-sided (0, 1) padding.
+int conv3x3_s2_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, int pad_lo,
+                    const EpilogueSpec& e, __half* out, int ldc, cudaStream_t st) {
+  TG_CHECK(Cin % 64 == 0 && Cout % 64 == 0 && H % 2 == 0 && W % 2 == 0, "conv3x3 s2: Cin/Cout multiples of 64, even H/W (got %d/%d %dx%d)",
+           Cin, Cout, H, W);
+  const int Ho = H / 2, Wo = W / 2;
+  int box_b, box_h, box_w;
+  if (conv_boxes(B, Ho, Wo, &box_b, &box_h, &box_w)) return -1;
+  GemmArgs g{};
+  g.M = B * Ho * Wo; g.N = Cout; g.K = 9 * Cin; g.K1 = g.K; g.mode = 1;
+  g.H = Ho; g.W = Wo; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
+  g.taps_w = 3; g.off_y = g.off_x = -pad_lo; g.in_stride = 2;
+  fill_args(g, e);
+  CUtensorMap a1;
+  if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, box_w, 2)) return -1;
+  return dispatch(a1, a1, g, Wt, out, ldc, st);
+}
+
+// nearest x2 upsample -> 3x3 convolution (diffusers Upsample2D) WITHOUT the upsampled tensor and with 2.25x fewer MACs:
+// output pixel (2i + py, 2j + px) only sees a 2 x 2 window of the low-resolution image, rows {i + py - 1, i + py} and
+// columns {j + px - 1, j + px}, with the 3x3 taps that land on the same input pixel summed (Wt4[py * 2 + px] =
+// [Cout, 2, 2, Cin], packed once by the host).  Four implicit GEMMs on the low-resolution grid, each storing its phase of
+// the [B, 2H, 2W, Cout] image through a 3D tensor map.
+int upsample2x_conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt4, int Cout, const EpilogueSpec& e,
+                            __half* out, cudaStream_t st) {
+  TG_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "upsample conv: Cin/Cout must be multiples of 64 (got %d/%d)", Cin, Cout);
+  TG_CHECK(e.residual == nullptr && e.rowbias == nullptr, "upsample conv: residual / row bias epilogues are not wired for phase outputs");
+  int box_b, box_h, box_w;
+  if (conv_boxes(B, H, W, &box_b, &box_h, &box_w)) return -1;
+  CUtensorMap a1;
+  if (make_tmap_nhwc(&a1, X, B, H, W, Cin, box_b, box_h, box_w)) return -1;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      GemmArgs g{};
+      g.M = B * H * W; g.N = Cout; g.K = 4 * Cin; g.K1 = g.K; g.mode = 1;
+      g.H = H; g.W = W; g.Cin = Cin; g.box_h = box_h; g.box_b = box_b;
+      g.taps_w = 2; g.off_y = py - 1; g.off_x = px - 1; g.in_stride = 1;
+      g.out3d_w = W;
+      fill_args(g, e);
+      const __half* wt = Wt4 + (size_t)(py * 2 + px) * Cout * 4 * Cin;
+      __half* o = out + ((size_t)py * 2 * W + px) * Cout;
+      if (dispatch(a1, a1, g, wt, o, Cout, st)) return -1;
+    }
+  return 0;
 }
 
 }  // namespace tg

@@ -102,20 +102,45 @@ int make_tmap_w_ky3(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 }
 
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C, uint32_t bb,
-                   uint32_t bh, uint32_t bw) {
+                   uint32_t bh, uint32_t bw, uint32_t pixel_stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (C * 2) % 16 == 0, "tmap nhwc: alignment");
   cuuint64_t dims[4] = {C, W, H, B};
   cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-  cuuint32_t box[4] = {64, bw, bh, bb};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // pixel_stride 2: the box gathers every other pixel in x and y (the traversal stride of the TMA unit) -- the operand
+  // of a stride-2 convolution without an im2col buffer.  The driver API counts boxDim in INPUT elements: to load n
+  // elements along a dimension with traversal stride s, boxDim = n * s.
+  cuuint32_t box[4] = {64, bw * pixel_stride, bh * pixel_stride, bb};
+  TG_CHECK(box[1] <= 256 && box[2] <= 256, "tmap nhwc: box %u x %u exceeds 256 with pixel stride %u", box[1], box[2], pixel_stride);
+  cuuint32_t estr[4] = {1, pixel_stride, pixel_stride, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(nhwc B=%llu H=%llu W=%llu C=%llu box=%u,%u,%u) -> %d",
            (unsigned long long)B, (unsigned long long)H, (unsigned long long)W, (unsigned long long)C, bb, bh, bw,
            (int)r);
+  return 0;
+}
+
+// Output of one (py, px) phase of "nearest x2 upsample -> 3x3 convolution" computed on the LOW-resolution grid: phase pixel
+// (b, i, j) lives at pixel (2i + py, 2j + px) of the [B, 2H, 2W, C] image.  `base` already points at pixel (py, px); seen
+// from there the phase image is [rows = B*H][W][C] with strides (4 W C, 2 C, 1) elements.  Store box: 32 channels x
+// box_w x box_r phase pixels = the 32 consecutive tile rows an epilogue warp stages (64-byte rows, 64B swizzle).
+int make_tmap_phase_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t W, uint64_t C, uint32_t box_w,
+                        uint32_t box_r) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  TG_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (C * 2) % 16 == 0, "tmap phase out: alignment");
+  cuuint64_t dims[3] = {C, W, rows};
+  cuuint64_t strides[2] = {2 * C * 2, 4 * W * C * 2};
+  cuuint32_t box[3] = {32, box_w, box_r};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(phase out rows=%llu W=%llu C=%llu box=%u,%u) -> %d",
+           (unsigned long long)rows, (unsigned long long)W, (unsigned long long)C, box_w, box_r, (int)r);
   return 0;
 }
 

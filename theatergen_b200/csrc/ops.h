@@ -22,6 +22,12 @@ int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, 
 // out[B*H*W, Cout] = epi( conv3x3_pad1(X[B,H,W,Cin]) ), Wt = [Cout, 3, 3, Cin]
 int conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, const EpilogueSpec& e,
                  __half* out, int ldc, cudaStream_t st);
+// out[B*(H/2)*(W/2), Cout] = epi( conv3x3_stride2(X[B,H,W,Cin]) ), padding (pad_lo, 1)
+int conv3x3_s2_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt, int Cout, int pad_lo,
+                    const EpilogueSpec& e, __half* out, int ldc, cudaStream_t st);
+// out[B,2H,2W,Cout] = epi( conv3x3_pad1(nearest_x2(X[B,H,W,Cin])) ) as four 2x2 convolutions; Wt4 = [4][Cout,2,2,Cin]
+int upsample2x_conv3x3_nhwc(const __half* X, int B, int H, int W, int Cin, const __half* Wt4, int Cout, const EpilogueSpec& e,
+                            __half* out, cudaStream_t st);
 
 
 // allocates the per-device split-K workspace (call once outside stream capture; lazily done otherwise)

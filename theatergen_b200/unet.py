@@ -17,7 +17,7 @@ import os
 import torch
 
 from . import _lib, ops
-from .weights import pack_conv3x3, pack_geglu
+from .weights import pack_conv3x3, pack_geglu, pack_upsample_conv3x3
 
 BLOCK_OUT = (320, 640, 1280, 1280)
 HEADS = 8
@@ -141,6 +141,23 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
     return t, rows
 
 
+def downsample_conv(x, w9, bias, cout, pad_lo=1, act=ops.TG_ACT_NONE):
+    """diffusers Downsample2D: 3x3 convolution, stride 2.  w9 = packed weight [Cout, 9*Cin] (the [Cout,3,3,Cin] tensor flattened).
+    Default: implicit GEMM with a stride-2 TMA gather; TG_CONV_S2=0 selects the im2col buffer + GEMM of round 1 (A/B)."""
+    B, H, W, cin = x.shape
+    if os.environ.get("TG_CONV_S2", "1") != "0":
+        return ops.conv3x3_s2(x, w9.view(cout, 3, 3, cin), bias, pad_lo=pad_lo, act=act)
+    return ops.gemm(ops.im2col_s2(x, pad_lo=pad_lo), w9, bias, act=act).view(B, H // 2, W // 2, cout)
+
+
+def upsample_conv(x, w, name):
+    """diffusers Upsample2D: nearest x2 + 3x3 convolution.  Default: four 2x2 convolutions on the low-resolution grid
+    (w[name + ".w4"], weights.pack_upsample_conv3x3); TG_UPCONV=0 selects upsample kernel + 3x3 convolution (A/B)."""
+    if os.environ.get("TG_UPCONV", "1") != "0":
+        return ops.upsample2x_conv3x3(x, w[name + ".w4"], w[name + ".b"])
+    return ops.conv3x3(ops.upsample2x(x), w[name + ".w"], w[name + ".b"])
+
+
 class _BlockNet:
     """Execution of the blocks the UNet and the ControlNet share (ResnetBlock2D, Transformer2DModel, the time
     embedding and the encoder half), on packed weights held in self.w / self.resnets / self.transformers."""
@@ -169,7 +186,7 @@ class _BlockNet:
                 skips.append(x)
             if i < 3:
                 c = BLOCK_OUT[i]
-                x = ops.gemm(ops.im2col_s2(x), w[f"down{i}.w"], w[f"down{i}.b"]).view(B, h_ // 2, w_ // 2, c)
+                x = downsample_conv(x, w[f"down{i}.w"], w[f"down{i}.b"], c)
                 h_, w_ = h_ // 2, w_ // 2
                 skips.append(x)
         return x, skips, h_, w_
@@ -283,7 +300,8 @@ class TGUNet(_BlockNet):
             w[f"down{i}.w"] = pack_conv3x3(g(f"down_blocks.{i}.downsamplers.0.conv.weight")).reshape(c, 9 * c)
             w[f"down{i}.b"] = g(f"down_blocks.{i}.downsamplers.0.conv.bias")
         for i in range(3):
-            w[f"up{i}.w"] = pack_conv3x3(g(f"up_blocks.{i}.upsamplers.0.conv.weight"))
+            w[f"up{i}.w"] = pack_conv3x3(g(f"up_blocks.{i}.upsamplers.0.conv.weight"))   # (guidance-gradient path)
+            w[f"up{i}.w4"] = pack_upsample_conv3x3(g(f"up_blocks.{i}.upsamplers.0.conv.weight"))
             w[f"up{i}.b"] = g(f"up_blocks.{i}.upsamplers.0.conv.bias")
         w["no.g"], w["no.b"] = g("conv_norm_out.weight"), g("conv_norm_out.bias")
         w["conv_out.w"], w["conv_out.b"] = pack_conv3x3(g("conv_out.weight")), g("conv_out.bias")
@@ -384,7 +402,7 @@ class TGUNet(_BlockNet):
                 if i > 0:
                     x = tf(f"up_blocks.{i}.attentions.{j}", x, h_, w_)
             if i < 3:
-                x = ops.conv3x3(ops.upsample2x(x), w[f"up{i}.w"], w[f"up{i}.b"])
+                x = upsample_conv(x, w, f"up{i}")
                 h_, w_ = 2 * h_, 2 * w_
         n = ops.groupnorm(x.view(B, h_ * w_, 320), w["no.g"], w["no.b"], 1e-5, silu=True)
         return ops.conv_out_tc(n.view(B, h_, w_, 320), w["conv_out.w64"], w["conv_out.b64"], 4)

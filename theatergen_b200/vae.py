@@ -24,8 +24,8 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from .unet import _getter
-from .weights import pack_conv3x3
+from .unet import _getter, downsample_conv, upsample_conv
+from .weights import pack_conv3x3, pack_upsample_conv3x3
 
 UP_CHANNELS = (512, 512, 256, 128)
 
@@ -110,6 +110,7 @@ class TGVAEDecoder(_VAEBlocks):
         _pack_attention(g, w, "decoder.mid_block.attentions.0")
         for i in range(3):
             w[f"up{i}.w"] = pack_conv3x3(g(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"))
+            w[f"up{i}.w4"] = pack_upsample_conv3x3(g(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"))
             w[f"up{i}.b"] = g(f"decoder.up_blocks.{i}.upsamplers.0.conv.bias")
         w["no.g"], w["no.b"] = g("decoder.conv_norm_out.weight"), g("decoder.conv_norm_out.bias")
         w["out.w"], w["out.b"] = pack_conv3x3(g("decoder.conv_out.weight")), g("decoder.conv_out.bias")
@@ -128,7 +129,7 @@ class TGVAEDecoder(_VAEBlocks):
             for j in range(3):
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x, B, H, W)
             if i < 3:
-                x = ops.conv3x3(ops.upsample2x(x), w[f"up{i}.w"], w[f"up{i}.b"])
+                x = upsample_conv(x, w, f"up{i}")
                 H, W = 2 * H, 2 * W
         n = ops.groupnorm(x.view(B, H * W, 128), w["no.g"], w["no.b"], 1e-6, silu=True)
         return ops.conv_out(n.view(B, H, W, 128), w["out.w"], w["out.b"])
@@ -180,7 +181,7 @@ class TGVAEEncoder(_VAEBlocks):
                 h = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", h, B, H, W)
             if i < 3:  # F.pad(h, (0,1,0,1)) + conv3x3 stride 2 pad 0
                 c = ENC_CHANNELS[i]
-                h = ops.gemm(ops.im2col_s2(h, pad_lo=0), w[f"down{i}.w"], w[f"down{i}.b"]).view(B, H // 2, W // 2, c)
+                h = downsample_conv(h, w[f"down{i}.w"], w[f"down{i}.b"], c, pad_lo=0)
                 H, W = H // 2, W // 2
         h = self._resnet("encoder.mid_block.resnets.0", h, B, H, W)
         h = self._attention(h, B, H, W)
