@@ -369,20 +369,18 @@ def run_ours(args):
         gme = MixedStepGraph(eng, K, 1, 81, KEYS, plan, controlnet=True).capture()
         gm = MixedStepGraph(eng, K, 1, 81, None, None, controlnet=True).capture()
         for g in (gme, gm):  # batch rows: [stage-1 uncond | stage-1 cond | stage-2 uncond | stage-2 cond]
-            g.ctx.copy_(torch.cat([ctx1, ctx2]))
+            g.set_context(torch.cat([ctx1, ctx2]), ctrl_ctx)   # context + its K / V projections: once per trajectory
             g.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2 + [0.1, 0.1]))
             g.latents.copy_(torch.cat([lat1, lat2]))
             g.mask.copy_(h_mask)
-            g.ctrl_ctx.copy_(ctrl_ctx)
         h_ctxm = pin(torch.cat([ctx1, ctx2]))
         h_ctrl = pin(ctrl_ctx)
         h_latm = pin(torch.cat([lat1, lat2]))
         h_tsm = pin(ts.cpu()[:, None].repeat(1, 2 * (K + 1)))
         h_outm = torch.empty((K + 1, 4, 64, 64), dtype=torch.float16).pin_memory()
-    g1.ctx.copy_(h_ctx1); g1.ip_scale.copy_(scale1); g1.latents.copy_(h_lat1)
+    g1.set_context(h_ctx1); g1.ip_scale.copy_(scale1); g1.latents.copy_(h_lat1)
     for g in (g2e, g2):
-        g.ctx.copy_(h_ctx2); g.ip_scale.fill_(0.1); g.latents.copy_(h_lat2); g.mask.copy_(h_mask)
-        g.ctrl_ctx.copy_(ctrl_ctx)
+        g.set_context(h_ctx2, ctrl_ctx); g.ip_scale.fill_(0.1); g.latents.copy_(h_lat2); g.mask.copy_(h_mask)
     stage2_graphs = (gme, gm) if mixed else (g2e, g2)
 
     def embed_hint(src):
@@ -402,8 +400,9 @@ def run_ours(args):
 
     def step_device_mixed(i):
         idx = i % STEPS
-        if idx == 0:
+        if idx == 0:  # per-trajectory work: hint embedder + K / V projections of the (device-resident) context
             embed_hint(d_hint)
+            gme.set_context(); gm.set_context()
         g = gme if idx < 30 else gm
         g.t.copy_(d_ts[idx].expand(2 * (K + 1))); g.coef.copy_(d_coef[idx]); g.frozen.copy_(d_frozen[idx + 1])
         g.replay()
@@ -416,10 +415,9 @@ def run_ours(args):
         idx = i % STEPS
         g = gme if idx < 30 else gm
         if idx == 0:
-            gme.ctx.copy_(h_ctxm, non_blocking=True); gm.ctx.copy_(h_ctxm, non_blocking=True)
+            gme.set_context(h_ctxm, h_ctrl); gm.set_context(h_ctxm, h_ctrl)   # H2D + K / V projection, once per trajectory
             gme.latents.copy_(h_latm, non_blocking=True); gme.mask.copy_(h_mask, non_blocking=True)
             gm.mask.copy_(h_mask, non_blocking=True)
-            gme.ctrl_ctx.copy_(h_ctrl, non_blocking=True); gm.ctrl_ctx.copy_(h_ctrl, non_blocking=True)
             d_hint.copy_(h_hint, non_blocking=True)
             embed_hint(d_hint)
         g.t.copy_(h_tsm[idx], non_blocking=True); g.coef.copy_(h_coef[idx], non_blocking=True)
@@ -437,6 +435,7 @@ def run_ours(args):
         idx = i % STEPS
         if idx == 0:
             embed_hint(d_hint)
+            g1.set_context(); g2e.set_context(); g2.set_context()
         g1.t.copy_(d_ts[idx].expand(2 * K)); g1.coef.copy_(d_coef[idx])
         g1.replay()
         g = g2e if idx < 30 else g2
@@ -455,9 +454,9 @@ def run_ours(args):
         idx = i % STEPS
         g1.t.copy_(h_ts8[idx], non_blocking=True); g1.coef.copy_(h_coef[idx], non_blocking=True)
         if idx == 0:
-            g1.ctx.copy_(h_ctx1, non_blocking=True); g1.latents.copy_(h_lat1, non_blocking=True)
+            g1.set_context(h_ctx1); g1.latents.copy_(h_lat1, non_blocking=True)
             for g in (g2e, g2):
-                g.ctx.copy_(h_ctx2, non_blocking=True); g.latents.copy_(h_lat2, non_blocking=True)
+                g.set_context(h_ctx2, h_ctrl if mixed else ctrl_ctx); g.latents.copy_(h_lat2, non_blocking=True)
                 g.mask.copy_(h_mask, non_blocking=True)
             d_hint.copy_(h_hint, non_blocking=True)
             embed_hint(d_hint)

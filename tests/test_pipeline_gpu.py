@@ -144,7 +144,7 @@ def test_full_config_properties():
     s4 = e1.step_graph(K, 81, False); s1 = e1.step_graph(1, 81, False)
     ts, coef = e1.tables(50, 7.5)
     for sg, l_, c_, sc_ in ((s4, lat, ctx, scale), (s1, lat[2:3], ctx[[2, K + 2]], scale[[2, K + 2]])):
-        sg.latents.copy_(l_); sg.ctx.copy_(c_); sg.ip_scale.copy_(sc_)
+        sg.latents.copy_(l_); sg.set_context(c_); sg.ip_scale.copy_(sc_)
         sg.t.copy_(ts[0].expand(sg.t.numel())); sg.coef.copy_(coef[0]); sg._body()
     d1 = (s4.latents[2].float() - s1.latents[0].float()).abs().max().item()
     assert d1 < 1e-2, d1
@@ -177,15 +177,15 @@ def test_cobatched_stage1_stage2_step_matches_separate_steps():
     ts, coef = eng.tables(50, 7.5)
     mx = MixedStepGraph(eng, K, 1, 81, keys, plan)
     # batch rows: [stage-1 uncond | stage-1 cond | stage-2 uncond | stage-2 cond]
-    mx.latents.copy_(torch.cat([lat1, lat2])); mx.ctx.copy_(torch.cat([ctx1, ctx2]))
+    mx.latents.copy_(torch.cat([lat1, lat2])); mx.set_context(torch.cat([ctx1, ctx2]))
     mx.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2 + [0.1, 0.1])); mx.frozen.copy_(frozen); mx.mask.copy_(mask.half())
     mx.t.copy_(ts[3].expand(10)); mx.coef.copy_(coef[3])
     mx._body()
     s1 = eng.step_graph(K, 81, False)
-    s1.latents.copy_(lat1); s1.ctx.copy_(ctx1); s1.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2))
+    s1.latents.copy_(lat1); s1.set_context(ctx1); s1.ip_scale.copy_(torch.tensor([0.0, 0.4, 0.4, 0.4] * 2))
     s1.t.copy_(ts[3].expand(8)); s1.coef.copy_(coef[3]); s1._body()
     s2 = eng.step_graph(1, 81, True, keys)
-    s2.latents.copy_(lat2); s2.ctx.copy_(ctx2); s2.ip_scale.fill_(0.1); s2.frozen.copy_(frozen); s2.mask.copy_(mask.half())
+    s2.latents.copy_(lat2); s2.set_context(ctx2); s2.ip_scale.fill_(0.1); s2.frozen.copy_(frozen); s2.mask.copy_(mask.half())
     s2.t.copy_(ts[3].expand(2)); s2.coef.copy_(coef[3]); s2._body()
     assert (mx.latents[:K].float() - s1.latents.float()).abs().max().item() < 1e-2
     assert (mx.latents[K:].float() - s2.latents.float()).abs().max().item() < 1e-2

@@ -130,13 +130,13 @@ class TGControlNet(_BlockNet):
                 h = downsample_conv(h, wt, bs, cout, act=ops.TG_ACT_SILU)
         return ops.conv3x3(h, w["ce.out.w"], w["ce.out.b"])
 
-    def encode(self, sample, t_dev, ctx, cond_emb):
+    def encode(self, sample, t_dev, ctx, cond_emb, ctxkv=None):
         """sample NCHW [B,4,64,64], t_dev float32 [B], ctx [B,77,768] (text only), cond_emb NHWC [n,64,64,320] (row b uses image b % n)
         -> (12 skip tensors, mid output), NHWC, BEFORE the zero-convolutions."""
         w = self.w
         B, _, H, W = sample.shape
         T = ctx.shape[1]
-        temb_all, ctxkv = self._time_and_context(t_dev, ctx.contiguous(), B)
+        temb_all, ctxkv = self._time_and_context(t_dev, ctx.contiguous(), B, ctxkv)  # ctxkv: project_context(ctx), optional
 
         def tf(p, x, h_, w_):
             return self._transformer(p, x, ctxkv, B, h_, w_, T, 0, None, None, None, False, None)

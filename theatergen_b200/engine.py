@@ -40,6 +40,12 @@ class StepGraph:
         self.capture_keys = capture_keys
         self.captured = {} if capture_keys else None
         self.engine = engine
+        # context K / V projections of every cross-attention layer: a function of `ctx` / `ctrl_ctx` only, refreshed by
+        # set_context() once per trajectory and read by every replayed step
+        self.ctxkv = torch.zeros((2 * K * T, engine.unet.w["ctxkv.w"].shape[0]), dtype=torch.float16, device=dev)
+        self.ctrl_ctxkv = None
+        if self.use_controlnet:
+            self.ctrl_ctxkv = torch.zeros((2 * K * 77, engine.controlnet.w["ctxkv.w"].shape[0]), dtype=torch.float16, device=dev)
         self.graph = None
         self.launches_per_step = 0
         self.replays = 0
@@ -47,14 +53,25 @@ class StepGraph:
     def _control(self, r0, r1):
         if not self.use_controlnet:
             return None, None
-        return self.engine.controlnet, dict(rows=(r0, r1), ctx=self.ctrl_ctx, cond_emb=self.cond_emb)
+        return self.engine.controlnet, dict(rows=(r0, r1), ctx=self.ctrl_ctx, cond_emb=self.cond_emb, ctxkv=self.ctrl_ctxkv)
+
+    def set_context(self, ctx=None, ctrl_ctx=None):
+        """Copy the trajectory's context into the graph's buffers (None: already there) and project it to the K / V of every
+        cross-attention layer -- once per trajectory, outside the replayed step."""
+        if ctx is not None:
+            self.ctx.copy_(ctx, non_blocking=True)
+        self.engine.unet.project_context(self.ctx, out=self.ctxkv)
+        if self.use_controlnet:
+            if ctrl_ctx is not None:
+                self.ctrl_ctx.copy_(ctrl_ctx, non_blocking=True)
+            self.engine.controlnet.project_context(self.ctrl_ctx, out=self.ctrl_ctxkv)
 
     def _body(self):
         net = self.engine.unet
         ops.duplicate_latents(self.latents, self.x_in)
         cn, control = self._control(0, 2 * self.K)
         eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
-                              save_keys=self.capture_keys, cond_only=True, controlnet=cn, control=control)
+                              save_keys=self.capture_keys, cond_only=True, controlnet=cn, control=control, ctxkv=self.ctxkv)
         ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
                                latents_copy=self.trace)
 
@@ -103,6 +120,7 @@ class MixedStepGraph(StepGraph):
                 raise RuntimeError("MixedStepGraph(controlnet=True) needs DenoiseEngine.controlnet (a TGControlNet)")
             self.ctrl_ctx = torch.zeros((2 * K2, 77, 768), dtype=torch.float16, device=dev)
             self.cond_emb = torch.zeros((K2, 64, 64, 320), dtype=torch.float16, device=dev)
+            self.ctrl_ctxkv = torch.zeros((2 * K2 * 77, engine.controlnet.w["ctxkv.w"].shape[0]), dtype=torch.float16, device=dev)
 
     def _body(self):
         net = self.engine.unet
@@ -111,7 +129,8 @@ class MixedStepGraph(StepGraph):
         ops.duplicate_latents(self.latents[K1:], self.x_in[2 * K1:])
         cn, control = self._control(2 * K1, 2 * (K1 + K2))
         eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
-                              save_keys=self.capture_keys, capture_b0=2 * K1 + K2, controlnet=cn, control=control)
+                              save_keys=self.capture_keys, capture_b0=2 * K1 + K2, controlnet=cn, control=control,
+                              ctxkv=self.ctxkv)
         if self.energy_plan is not None:
             self.energy_plan.run([self.captured[k][0] for k in self.capture_keys], self.loss, self._ws)
         ops.cfg_ddim_composite(eps[:2 * K1], self.latents[:K1], self.coef, latents_copy=self.trace[:K1])
@@ -166,9 +185,8 @@ class DenoiseEngine:
         use_cn = control_ctx is not None
         sg = self.step_graph(K, T, composite, capture_keys, controlnet=use_cn)
         sg.latents.copy_(latents, non_blocking=True)
-        sg.ctx.copy_(ctx, non_blocking=True)
+        sg.set_context(ctx, control_ctx if use_cn else None)
         if use_cn:
-            sg.ctrl_ctx.copy_(control_ctx, non_blocking=True)
             sg.cond_emb.copy_(cond_emb.expand_as(sg.cond_emb), non_blocking=True)
         if torch.is_tensor(ip_scale):
             sg.ip_scale.copy_(ip_scale.to(torch.float32), non_blocking=True)
@@ -185,9 +203,8 @@ class DenoiseEngine:
                 if sg_plain is None:
                     sg_plain = self.step_graph(K, T, False, capture_keys, controlnet=use_cn)
                     if use_cn:
-                        sg_plain.ctrl_ctx.copy_(sg.ctrl_ctx)
                         sg_plain.cond_emb.copy_(sg.cond_emb)
-                    sg_plain.ctx.copy_(sg.ctx)
+                    sg_plain.set_context(sg.ctx, sg.ctrl_ctx if use_cn else None)
                     sg_plain.ip_scale.copy_(sg.ip_scale)
                     sg_plain.latents.copy_(sg.latents)
                 cur = sg_plain

@@ -163,13 +163,21 @@ class _BlockNet:
     embedding and the encoder half), on packed weights held in self.w / self.resnets / self.transformers."""
     dtype = torch.float16
 
-    def _time_and_context(self, t_dev, ctx, B):
+    def project_context(self, ctx, out=None):
+        """K / V projections of the context tokens for every cross-attention layer in one GEMM: [B, T, 768] ->
+        [B*T, sum of 2C (text) + 2C (image tokens) per layer].  They depend on the prompt / image tokens only -- not on the
+        timestep or the latents -- so a denoise loop computes them ONCE per trajectory (engine.StepGraph.set_context)
+        instead of once per step like the reference's processors do (attention_processor.py:475-476, 497-498): same values."""
+        return ops.gemm(ctx.reshape(ctx.shape[0] * ctx.shape[1], -1), self.w["ctxkv.w"], out=out)
+
+    def _time_and_context(self, t_dev, ctx, B, ctxkv=None):
         w = self.w
         emb = ops.timestep_embedding(t_dev, 320)
         emb = ops.gemm(emb, w["t1.w"], w["t1.b"], act=ops.TG_ACT_SILU)
         emb = ops.gemm(emb, w["t2.w"], w["t2.b"], act=ops.TG_ACT_SILU)  # = silu(time_embedding(t)), its only use
         temb_all = ops.gemm(emb, w["temb.w"], w["temb.b"])
-        ctxkv = ops.gemm(ctx.reshape(B * ctx.shape[1], -1), w["ctxkv.w"])
+        if ctxkv is None:
+            ctxkv = self.project_context(ctx)
         return temb_all, ctxkv
 
     def _encoder(self, x, temb_all, tf, B, H, W):
@@ -346,14 +354,17 @@ class TGUNet(_BlockNet):
 
     # -------------------------------------------------------------------------------------------------
     def forward_raw(self, sample, t_dev, ctx, ip_scale=None, down_residuals=None, mid_residual=None, capture=None,
-                    save_keys=None, cond_only=False, token_idx=None, capture_b0=None, controlnet=None, control=None):
+                    save_keys=None, cond_only=False, token_idx=None, capture_b0=None, controlnet=None, control=None,
+                    ctxkv=None):
         """sample [B,4,H,W] fp16 (B even), t_dev float32 [B] on device, ctx [B,T,768] fp16 -> eps [B,4,H,W].
 
         ControlNet residuals arrive either as NCHW tensors (down_residuals / mid_residual: the reference call
         surface, ip_adapter/unet_2d_condition.py:1044-1053, 1077-1078) or fused: `controlnet` (a TGControlNet) with
         `control = dict(rows=(r0, r1), ctx=[r1-r0,77,768], cond_emb=...)` runs the ControlNet encoder on batch rows
         [r0, r1) of this very forward and its zero-convolutions add straight into the skip tensors (GEMM epilogue).
-        capture_b0: first batch row whose text-attention probabilities are captured (default B/2 when cond_only)."""
+        capture_b0: first batch row whose text-attention probabilities are captured (default B/2 when cond_only).
+        ctxkv: `project_context(ctx)` computed by the caller (once per trajectory); `control["ctxkv"]` likewise for the
+        ControlNet's text context."""
         w = self.w
         B, _, H, W = sample.shape
         assert B % 2 == 0, "co-batched CFG pairs: batch must be even"
@@ -362,7 +373,7 @@ class TGUNet(_BlockNet):
         n_text = T - n_ip
         if n_ip and ip_scale is None:
             ip_scale = self._ip_scale_tensor(B)
-        temb_all, ctxkv = self._time_and_context(t_dev, ctx, B)
+        temb_all, ctxkv = self._time_and_context(t_dev, ctx, B, ctxkv)
 
         def tf(p, x, h_, w_):
             return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
@@ -374,7 +385,8 @@ class TGUNet(_BlockNet):
             # join before its residuals are added.  Under CUDA-graph capture the two become parallel graph branches.
             r0, r1 = control["rows"]
             if os.environ.get("TG_CN_OVERLAP", "1") == "0":  # A/B measurements: ControlNet in line on the main stream
-                ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
+                ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"],
+                                         ctxkv=control.get("ctxkv"))
             else:
                 main = torch.cuda.current_stream()
                 side = self._side_stream()
@@ -382,7 +394,8 @@ class TGUNet(_BlockNet):
                 _lib.check(_lib.lib().tg_gemm_set_scratch_slot(1), "tg_gemm_set_scratch_slot")  # own split-K workspace
                 try:
                     with torch.cuda.stream(side):
-                        ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"])
+                        ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"],
+                                                 ctxkv=control.get("ctxkv"))
                 finally:
                     _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
         x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
