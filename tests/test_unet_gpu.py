@@ -119,3 +119,43 @@ def test_same_gpu_eager_reference_timing():
             out[(name, B)] = (time.perf_counter() - t0) / reps * 1e3
     print("same-GPU forward time, ms:", {f"{k[0]} B={k[1]}": round(v, 2) for k, v in out.items()})
     assert out[("ours_eager", 10)] < out[("torch_eager_fp16", 10)]
+
+
+def test_cfg_prefix_sharing_equals_duplicated_rows():
+    """forward_raw(unique=...) computes the context-independent prefix (conv_in, first ResnetBlock2D, first self-attention)
+    once per trajectory; the result is the duplicated-rows computation up to batch-size-dependent fp16 rounding
+    (different tile / split choices for B = K vs 2K), both within the oracle tolerance.  With and without ControlNet."""
+    from oracle import controlnet as OC
+    from theatergen_b200.controlnet import TGControlNet
+    from theatergen_b200.unet import TGUNet
+    OU, sd, x, ctx = _setup(4, seed=3)
+    K = 2
+    lat = x[:K].cuda()
+    xin = torch.cat([lat, lat])
+    ar = torch.arange(K, device="cuda")
+    src = torch.cat([ar, ar])
+    net = TGUNet(sd)
+    t_dev = torch.full((4,), 621.0, dtype=torch.float32, device="cuda")
+    scale = torch.full((4,), 0.3, dtype=torch.float32, device="cuda")
+    a = net.forward_raw(xin, t_dev, ctx.cuda(), ip_scale=scale)
+    b = net.forward_raw(xin, t_dev, ctx.cuda(), ip_scale=scale, unique=(lat, src, ar))
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref32 = OU.unet_forward(sd32, xin.float(), 621, ctx.float().cuda(), ip_scale=0.3)
+    ra, rb = _report("duplicated", a, ref32), _report("shared prefix", b, ref32)
+    assert (a.float() - b.float()).abs().max().item() <= 4e-3
+    assert rb["max_abs"] <= max(1.5 * ra["max_abs"], 4e-3) and rb["rel_rms"] <= 2e-3
+    # rows of one trajectory still differ (their contexts do)
+    assert (b[0].float() - b[K].float()).abs().max().item() > 1e-3
+    # ControlNet branch with the same sharing
+    cn = TGControlNet(OC.synth_state_dict(4321))
+    g = torch.Generator().manual_seed(5)
+    cond = torch.rand(1, 3, 512, 512, generator=g).half().cuda()
+    ctx_text = torch.randn(4, 77, 768, generator=g).half().cuda()
+    emb = cn.embed_condition(cond)
+    c = net.forward_raw(xin, t_dev, ctx.cuda(), ip_scale=scale, controlnet=cn,
+                        control=dict(rows=(0, 4), ctx=ctx_text, cond_emb=emb))
+    d = net.forward_raw(xin, t_dev, ctx.cuda(), ip_scale=scale, controlnet=cn, unique=(lat, src, ar),
+                        control=dict(rows=(0, 4), ctx=ctx_text, cond_emb=emb, share=(src, ar)))
+    assert (c.float() - d.float()).abs().max().item() <= 4e-3
+    assert (c.float() - a.float()).abs().max().item() > 1e-3  # the residuals do something

@@ -130,7 +130,7 @@ class TGControlNet(_BlockNet):
                 h = downsample_conv(h, wt, bs, cout, act=ops.TG_ACT_SILU)
         return ops.conv3x3(h, w["ce.out.w"], w["ce.out.b"])
 
-    def encode(self, sample, t_dev, ctx, cond_emb, ctxkv=None):
+    def encode(self, sample, t_dev, ctx, cond_emb, ctxkv=None, share=None):
         """sample NCHW [B,4,64,64], t_dev float32 [B], ctx [B,77,768] (text only), cond_emb NHWC [n,64,64,320] (row b uses image b % n)
         -> (12 skip tensors, mid output), NHWC, BEFORE the zero-convolutions."""
         w = self.w
@@ -138,12 +138,24 @@ class TGControlNet(_BlockNet):
         T = ctx.shape[1]
         temb_all, ctxkv = self._time_and_context(t_dev, ctx.contiguous(), B, ctxkv)  # ctxkv: project_context(ctx), optional
 
-        def tf(p, x, h_, w_):
-            return self._transformer(p, x, ctxkv, B, h_, w_, T, 0, None, None, None, False, None)
+        def tf(p, x, h_, w_, share=None):
+            return self._transformer(p, x, ctxkv, B, h_, w_, T, 0, None, None, None, False, None, share=share)
 
-        x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
         per = H * W * 320
         n = cond_emb.shape[0]  # 1 (one image), K (rows [uncond K | cond K] share the K images) or B
+        if share is not None:
+            # CFG prefix sharing (unet._BlockNet._encoder): rows [uncond K | cond K] carry the same latents, timestep and
+            # hint image, so conv_in + hint, the first ResnetBlock2D and the first self-attention run on the K unique rows
+            src, first = share
+            U = first.numel()
+            assert B == 2 * U and n in (1, U), "shared prefix expects rows [uncond K | cond K] and one hint per trajectory"
+            x = ops.conv_in_gemm(sample[:U].contiguous(), w["conv_in.w"], w["conv_in.b"])
+            for b in range(U):
+                ops.add_inplace(x.view(-1)[b * per:(b + 1) * per], cond_emb[b % n].reshape(-1))
+            x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W, share=share)
+            x = self._mid(x, temb_all, tf, B, h_, w_)
+            return skips, x
+        x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
         for b in range(B):  # + conditioning embedding
             ops.add_inplace(x.view(-1)[b * per:(b + 1) * per], cond_emb[b % n].reshape(-1))
         x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)

@@ -9,6 +9,8 @@ copy that is only waited for at the end of the trajectory.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -49,11 +51,22 @@ class StepGraph:
         self.graph = None
         self.launches_per_step = 0
         self.replays = 0
+        # CFG prefix sharing (unet._BlockNet._encoder): batch row -> trajectory, trajectory -> one of its batch rows
+        self.share_prefix = os.environ.get("TG_CFG_SHARE", "1") != "0"
+        ar = torch.arange(K, device=dev)
+        self.src, self.first = torch.cat([ar, ar]), ar.clone()
+        self._ctrl_share = None
 
     def _control(self, r0, r1):
         if not self.use_controlnet:
             return None, None
-        return self.engine.controlnet, dict(rows=(r0, r1), ctx=self.ctrl_ctx, cond_emb=self.cond_emb, ctxkv=self.ctrl_ctxkv)
+        c = dict(rows=(r0, r1), ctx=self.ctrl_ctx, cond_emb=self.cond_emb, ctxkv=self.ctrl_ctxkv)
+        if self.share_prefix:
+            if self._ctrl_share is None:  # ControlNet rows [uncond k | cond k] -> its k unique rows (built before capture)
+                ar = torch.arange((r1 - r0) // 2, device=self.latents.device)
+                self._ctrl_share = (torch.cat([ar, ar]), ar)
+            c["share"] = self._ctrl_share
+        return self.engine.controlnet, c
 
     def set_context(self, ctx=None, ctrl_ctx=None):
         """Copy the trajectory's context into the graph's buffers (None: already there) and project it to the K / V of every
@@ -71,7 +84,8 @@ class StepGraph:
         ops.duplicate_latents(self.latents, self.x_in)
         cn, control = self._control(0, 2 * self.K)
         eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
-                              save_keys=self.capture_keys, cond_only=True, controlnet=cn, control=control, ctxkv=self.ctxkv)
+                              save_keys=self.capture_keys, cond_only=True, controlnet=cn, control=control, ctxkv=self.ctxkv,
+                              unique=(self.latents, self.src, self.first) if self.share_prefix else None)
         ops.cfg_ddim_composite(eps, self.latents, self.coef, frozen=self.frozen, mask=self.mask,
                                latents_copy=self.trace)
 
@@ -121,6 +135,10 @@ class MixedStepGraph(StepGraph):
             self.ctrl_ctx = torch.zeros((2 * K2, 77, 768), dtype=torch.float16, device=dev)
             self.cond_emb = torch.zeros((K2, 64, 64, 320), dtype=torch.float16, device=dev)
             self.ctrl_ctxkv = torch.zeros((2 * K2 * 77, engine.controlnet.w["ctxkv.w"].shape[0]), dtype=torch.float16, device=dev)
+        # rows [stage-1 uncond K1 | stage-1 cond K1 | stage-2 uncond K2 | stage-2 cond K2] -> trajectory index into `latents`
+        a1, a2 = torch.arange(K1, device=dev), K1 + torch.arange(K2, device=dev)
+        self.src = torch.cat([a1, a1, a2, a2])
+        self.first = torch.cat([a1, 2 * K1 + torch.arange(K2, device=dev)])
 
     def _body(self):
         net = self.engine.unet
@@ -130,7 +148,7 @@ class MixedStepGraph(StepGraph):
         cn, control = self._control(2 * K1, 2 * (K1 + K2))
         eps = net.forward_raw(self.x_in, self.t, self.ctx, ip_scale=self.ip_scale, capture=self.captured,
                               save_keys=self.capture_keys, capture_b0=2 * K1 + K2, controlnet=cn, control=control,
-                              ctxkv=self.ctxkv)
+                              ctxkv=self.ctxkv, unique=(self.latents, self.src, self.first) if self.share_prefix else None)
         if self.energy_plan is not None:
             self.energy_plan.run([self.captured[k][0] for k in self.capture_keys], self.loss, self._ws)
         ops.cfg_ddim_composite(eps[:2 * K1], self.latents[:K1], self.coef, latents_copy=self.trace[:K1])

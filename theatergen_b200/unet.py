@@ -180,14 +180,32 @@ class _BlockNet:
             ctxkv = self.project_context(ctx)
         return temb_all, ctxkv
 
-    def _encoder(self, x, temb_all, tf, B, H, W):
+    def _encoder(self, x, temb_all, tf, B, H, W, share=None):
         """conv_in output -> (last down output, 12 skip tensors, h, w): CrossAttnDownBlock2D x3 + DownBlock2D
-        (ip_adapter/unet_2d_blocks.py:1045-1116, 1171-1202)."""
+        (ip_adapter/unet_2d_blocks.py:1045-1116, 1171-1202).
+
+        share = (src, first): CFG prefix sharing.  The unconditional and the conditional row of a trajectory enter the network
+        with the SAME latents and timestep (`torch.cat([latents] * 2)`, models/pipelines.py:409, 747) and differ only in the
+        context, which the network first looks at in the cross-attention of down_blocks.0.attentions.0.  Everything before it
+        -- conv_in, the first ResnetBlock2D, GroupNorm, proj_in and the whole 64x64 self-attention of the first transformer --
+        is therefore identical for the two rows and is computed once per trajectory: `x` holds the U unique rows,
+        `src[b]` is the unique row of batch row b (device int64 [B]) and `first[u]` a batch row that carries unique row u's
+        timestep (device int64 [U]).  Same values as the duplicated computation, half the work for that prefix."""
         w = self.w
-        skips = [x]
         h_, w_ = H, W
+        if share is not None:
+            src, first = share
+            U = x.shape[0]
+            skips = [x.index_select(0, src)]
+            xu = self._resnet("down_blocks.0.resnets.0", x, None, temb_all.index_select(0, first), U, h_, w_)
+            x = tf("down_blocks.0.attentions.0", xu, h_, w_, share=src)
+            skips.append(x)
+        else:
+            skips = [x]
         for i in range(4):
             for j in range(2):
+                if share is not None and i == 0 and j == 0:
+                    continue
                 x = self._resnet(f"down_blocks.{i}.resnets.{j}", x, None, temb_all, B, h_, w_)
                 if i < 3:
                     x = tf(f"down_blocks.{i}.attentions.{j}", x, h_, w_)
@@ -223,22 +241,28 @@ class _BlockNet:
         return ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc)
 
     def _transformer(self, p, x, ctxkv, B, H, W, n_text, n_ip, ip_scale, capture, save_keys, cond_only, token_idx,
-                     capture_b0=None):
+                     capture_b0=None, share=None):
+        """share (device int64 [B], CFG prefix sharing, see _encoder): `x` holds U unique rows; GroupNorm, proj_in and the
+        self-attention run on them once and are expanded to the B batch rows in front of the cross-attention."""
         t = self.transformers[p]
-        C, M = t["C"], B * H * W
-        n = ops.groupnorm(x.view(B, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
-        h = ops.gemm(n.view(M, C), t["piw"], t["pib"])
+        Bu = x.shape[0] if share is not None else B   # rows the context-independent part runs on
+        C, M, Mu = t["C"], B * H * W, Bu * H * W
+        n = ops.groupnorm(x.view(Bu, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
+        h = ops.gemm(n.view(Mu, C), t["piw"], t["pib"])
         # self attention
         ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
         qkv = ops.gemm(ln, t["qkvw"])
         if t["qkv_pad"] and (H * W) % 128 == 0:
             P = HEADS * t["qkv_pad"]
-            a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], B, HEADS, C // HEADS)
+            a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], Bu, HEADS, C // HEADS)
         elif t["qkv_pad"]:
             raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
         else:
-            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, HEADS)
+            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS)
         h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
+        if share is not None:  # from here on the two rows of a trajectory see different context tokens
+            h = h.view(Bu, H * W * C).index_select(0, share).view(M, C)
+            x = x.view(Bu, H * W * C).index_select(0, share)
         # cross attention (+ image tokens)
         ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
         q = ops.gemm(ln, t["q2w"])
@@ -355,7 +379,7 @@ class TGUNet(_BlockNet):
     # -------------------------------------------------------------------------------------------------
     def forward_raw(self, sample, t_dev, ctx, ip_scale=None, down_residuals=None, mid_residual=None, capture=None,
                     save_keys=None, cond_only=False, token_idx=None, capture_b0=None, controlnet=None, control=None,
-                    ctxkv=None):
+                    ctxkv=None, unique=None):
         """sample [B,4,H,W] fp16 (B even), t_dev float32 [B] on device, ctx [B,T,768] fp16 -> eps [B,4,H,W].
 
         ControlNet residuals arrive either as NCHW tensors (down_residuals / mid_residual: the reference call
@@ -364,7 +388,9 @@ class TGUNet(_BlockNet):
         [r0, r1) of this very forward and its zero-convolutions add straight into the skip tensors (GEMM epilogue).
         capture_b0: first batch row whose text-attention probabilities are captured (default B/2 when cond_only).
         ctxkv: `project_context(ctx)` computed by the caller (once per trajectory); `control["ctxkv"]` likewise for the
-        ControlNet's text context."""
+        ControlNet's text context.
+        unique = (sample_u [U,4,H,W], src int64 [B], first int64 [U]): CFG prefix sharing (see _encoder) -- `sample` must be
+        sample_u[src]; `control["share"] = (src, first)` relative to the ControlNet's rows likewise."""
         w = self.w
         B, _, H, W = sample.shape
         assert B % 2 == 0, "co-batched CFG pairs: batch must be even"
@@ -375,9 +401,9 @@ class TGUNet(_BlockNet):
             ip_scale = self._ip_scale_tensor(B)
         temb_all, ctxkv = self._time_and_context(t_dev, ctx, B, ctxkv)
 
-        def tf(p, x, h_, w_):
+        def tf(p, x, h_, w_, share=None):
             return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
-                                     token_idx, capture_b0)
+                                     token_idx, capture_b0, share=share)
 
         ctrl = side = None
         if controlnet is not None:
@@ -386,7 +412,7 @@ class TGUNet(_BlockNet):
             r0, r1 = control["rows"]
             if os.environ.get("TG_CN_OVERLAP", "1") == "0":  # A/B measurements: ControlNet in line on the main stream
                 ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"],
-                                         ctxkv=control.get("ctxkv"))
+                                         ctxkv=control.get("ctxkv"), share=control.get("share"))
             else:
                 main = torch.cuda.current_stream()
                 side = self._side_stream()
@@ -395,11 +421,15 @@ class TGUNet(_BlockNet):
                 try:
                     with torch.cuda.stream(side):
                         ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"],
-                                                 ctxkv=control.get("ctxkv"))
+                                                 ctxkv=control.get("ctxkv"), share=control.get("share"))
                 finally:
                     _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
-        x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
-        x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
+        if unique is not None:
+            x = ops.conv_in_gemm(unique[0], w["conv_in.w"], w["conv_in.b"])
+            x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W, share=(unique[1], unique[2]))
+        else:
+            x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
+            x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
         if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
             skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
         x = self._mid(x, temb_all, tf, B, h_, w_)
