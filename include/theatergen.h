@@ -111,6 +111,20 @@ int tg_attn_set_variant(int v);
  * <= 64 and the mma.sync kernel above (each where it measured faster), 0 mma.sync everywhere, 1 tcgen05 everywhere. */
 int tg_attn_cross_set_impl(int mode);
 
+/* GroupNorm without the statistics pass.  tg_gemm_set_stats(stats, rows_per_image) arms the NEXT tg_gemm / tg_conv3x3 /
+ * tg_conv3x3_s2 / tg_upsample2x_conv3x3 call of the calling host thread (one shot; NULL disarms): its epilogue also adds, per
+ * (image = row / rows_per_image, pair of adjacent output columns), 2^24 x (sum, sum of squares) of the fp16 values it
+ * stores to stats[image][column / 2][0..1] (64-bit integers, caller-zeroed; integer atomics, so the totals are
+ * independent of the arrival order -- bit-reproducible).  rows_per_image: a multiple of 32 dividing M; not with GEGLU.
+ * tg_groupnorm_apply normalises (+SiLU) [x1 | x2] from such totals in one pass: the same function as tg_groupnorm (diffusers
+ * ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out; ip_adapter/unet_2d_blocks.py, transformer_2d.py:288,
+ * unet_2d_condition.py:1117-1119).  statsN_alt (may be NULL): images [alt_b0, alt_b1) of that input take their totals from
+ * statsN_alt[image - alt_b0] -- rows a later in-place GEMM (the ControlNet residual add) rewrote and re-measured. */
+int tg_gemm_set_stats(long long* stats, int rows_per_image);
+int tg_groupnorm_apply(const tg_half* x1, int C1, const long long* stats1, const long long* stats1_alt, const tg_half* x2, int C2,
+                       const long long* stats2, const long long* stats2_alt, int alt_b0, int alt_b1, int B, int HW,
+                       const tg_half* gamma, const tg_half* beta, float eps, int silu, tg_half* out, void* stream);
+
 /* Launch-geometry knobs of tg_groupnorm for measurements (values <= 0 keep the current setting; fused: 1 allows the
  * single-kernel cluster path for tensors whose per-image slab fits on chip, 0 forces the two-pass kernels, <0 keeps).
  * No reference counterpart (the reference leaves this to ATen). */

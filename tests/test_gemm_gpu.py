@@ -218,3 +218,99 @@ def test_upsample2x_conv3x3_four_phases(B, H, Cin, Cout):
     _close(out, ref, 3e-3, 3e-3)
     old = ops.conv3x3(ops.upsample2x(x), w.permute(0, 2, 3, 1).contiguous(), bias)
     assert (out.float() - old.float()).abs().max().item() < 4e-3
+
+
+def _totals(out, images):
+    """Reference GroupNorm totals of a stored fp16 tensor [M, N]: [images, N/2, 2] (sum, sum of squares) in float64."""
+    v = out.double().view(images, -1, out.shape[-1] // 2, 2)
+    return torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1)
+
+
+def _check_totals(stats, out2d, images):
+    got = stats.double() / 2.0 ** 24
+    ref = _totals(out2d, images)
+    err = (got - ref).abs()
+    tol = 1e-5 * ref.abs() + 1e-3  # fp32 partial sums over 64 values, 2^-24 fixed point
+    assert bool((err <= tol).all()), (err.max().item(), ref.abs().max().item())
+
+
+def test_groupnorm_totals_from_the_gemm_epilogue():
+    """tg_gemm_set_stats: the epilogue of a linear / convolution / stride-2 convolution / upsample convolution (plain and
+    split-K tiles, CTA pairs and single CTAs, residual and row-bias epilogues) accumulates per (image, channel pair) the sum
+    and sum of squares of the fp16 values it stores; integer atomics -> two runs give identical bits."""
+    from theatergen_b200 import ops
+    from theatergen_b200.weights import pack_upsample_conv3x3
+    # linear, 4 images x 1024 rows (pair tiles) and 2 images x 64 rows (one M tile spans both images; split-K: K = 5120)
+    for (imgs, hw, N, K, seed) in [(4, 1024, 320, 320, 1), (2, 64, 1280, 5120, 2), (10, 256, 640, 640, 3)]:
+        M = imgs * hw
+        a, w = _rand((M, K), seed), _rand((N, K), seed + 10, K ** -0.5)
+        res, bias = _rand((M, N), seed + 20), _rand((N,), seed + 30)
+        st = torch.zeros((imgs, N // 2, 2), dtype=torch.int64, device="cuda")
+        out = ops.gemm(a, w, bias, residual=res, stats=st)
+        assert torch.equal(out, ops.gemm(a, w, bias, residual=res)), "the statistics epilogue must not change the output"
+        _check_totals(st, out, imgs)
+        st2 = torch.zeros_like(st)
+        ops.gemm(a, w, bias, residual=res, stats=st2)
+        assert torch.equal(st, st2), "totals must be bit-reproducible"
+        st3 = torch.zeros_like(st)  # one-shot: the next launch is not armed
+        ops.gemm(a, w, bias, residual=res)
+        assert int(st3.abs().sum()) == 0
+    # convolutions
+    B, H, Cin, Cout = 2, 32, 128, 192
+    x = _rand((B, H, H, Cin), 4)
+    w = _rand((Cout, 3, 3, Cin), 5, (9 * Cin) ** -0.5)
+    rb = _rand((B, Cout), 6)
+    st = torch.zeros((B, Cout // 2, 2), dtype=torch.int64, device="cuda")
+    out = ops.conv3x3(x, w, None, rowbias=rb, stats=st)
+    _check_totals(st, out.view(-1, Cout), B)
+    st = torch.zeros((B, Cout // 2, 2), dtype=torch.int64, device="cuda")
+    out = ops.conv3x3_s2(x, w, None, stats=st)
+    _check_totals(st, out.view(-1, Cout), B)
+    st = torch.zeros((B, Cout // 2, 2), dtype=torch.int64, device="cuda")
+    w4 = pack_upsample_conv3x3(_rand((Cout, Cin, 3, 3), 7, (9 * Cin) ** -0.5))
+    out = ops.upsample2x_conv3x3(x, w4, None, stats=st)
+    _check_totals(st, out.view(-1, Cout), B)
+    # low resolution, long K (split-K last-arriver epilogue), 8x8 images: a 128-row tile holds two images
+    B, H, Cin, Cout = 4, 8, 1280, 1280
+    x = _rand((B, H, H, Cin), 8)
+    w = _rand((Cout, 3, 3, Cin), 9, (9 * Cin) ** -0.5)
+    st = torch.zeros((B, Cout // 2, 2), dtype=torch.int64, device="cuda")
+    out = ops.conv3x3(x, w, None, stats=st)
+    _check_totals(st, out.view(-1, Cout), B)
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu", [(10, 4096, 320, 0, True), (4, 1024, 640, 320, True), (2, 64, 1280, 1280, True),
+                                             (3, 256, 1280, 640, False), (4, 4096, 320, 320, True)])
+def test_groupnorm_apply_from_totals(B, HW, C1, C2, silu):
+    """tg_groupnorm_apply (one pass, statistics from the producers' epilogues) == tg_groupnorm (self-measuring kernels) on
+    the same tensors, for single and concatenated inputs (group boundaries straddling the two tensors: C = 960, 1920), and
+    with the rows [b0, b1) of both inputs re-measured (ControlNet residual add)."""
+    from theatergen_b200 import ops
+
+    def produce(Bn, C, seed):
+        a, w = _rand((Bn * HW, 64), seed, 2.0), _rand((C, 64), seed + 1, 0.3)
+        st = torch.zeros((Bn, C // 2, 2), dtype=torch.int64, device="cuda")
+        return ops.gemm(a, w, _rand((C,), seed + 2), stats=st).view(Bn, HW, C), st
+
+    x1, s1 = produce(B, C1, 1)
+    x2, s2 = produce(B, C2, 5) if C2 else (None, None)
+    g, b = _rand((C1 + C2,), 9), _rand((C1 + C2,), 10)
+    ref = ops.groupnorm(x1, g, b, 1e-5, x2=x2, silu=silu)
+    got = ops.groupnorm(x1, g, b, 1e-5, x2=x2, silu=silu, st1=ops.GnStats(s1), st2=None if x2 is None else ops.GnStats(s2))
+    assert (got.float() - ref.float()).abs().max().item() <= 4e-3
+    xf = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+    r32 = F.group_norm(xf.permute(0, 2, 1), 32, g.float(), b.float(), 1e-5).permute(0, 2, 1)
+    r32 = F.silu(r32) if silu else r32
+    assert (got.float() - r32).abs().max().item() <= 6e-3
+    if B >= 3:  # rows [1, 3) rewritten in place by a residual GEMM that re-measures them
+        def rewrite(x, s, C, seed):
+            a, w = _rand((2 * HW, 64), seed), _rand((C, 64), seed + 1, 0.5)
+            dst = x[1:3].view(-1, C)
+            alt = torch.zeros((2, C // 2, 2), dtype=torch.int64, device="cuda")
+            ops.gemm(a, w, residual=dst, out=dst, stats=alt)
+            return ops.GnStats(s, alt, 1, 3)
+        t1 = rewrite(x1, s1, C1, 20)
+        t2 = rewrite(x2, s2, C2, 30) if C2 else None
+        ref = ops.groupnorm(x1, g, b, 1e-5, x2=x2, silu=silu)
+        got = ops.groupnorm(x1, g, b, 1e-5, x2=x2, silu=silu, st1=t1, st2=t2)
+        assert (got.float() - ref.float()).abs().max().item() <= 4e-3

@@ -159,3 +159,55 @@ def test_cfg_prefix_sharing_equals_duplicated_rows():
                         control=dict(rows=(0, 4), ctx=ctx_text, cond_emb=emb, share=(src, ar)))
     assert (c.float() - d.float()).abs().max().item() <= 4e-3
     assert (c.float() - a.float()).abs().max().item() > 1e-3  # the residuals do something
+
+
+def test_groupnorm_totals_reach_every_site():
+    """Every GroupNorm of the 64x64 and 32x32 levels of the UNet forward (31 of 61) and of the fused ControlNet branch (11) is
+    fed by epilogue totals, and at every
+    site the one-pass result equals the self-measuring kernels' on the same tensor (ops.GN_CHECK_LOG runs both) -- with the
+    shared CFG prefix and with ControlNet residuals rewriting rows of the skip tensors.  Also: TG_GN_STATS=0 gives the same
+    eps up to fp16 rounding, and two runs are bit-identical (integer atomics)."""
+    import os
+    from oracle import controlnet as OC
+    from theatergen_b200 import ops
+    from theatergen_b200.controlnet import TGControlNet
+    from theatergen_b200.unet import TGUNet
+    OU, sd, x, ctx = _setup(6, seed=7)
+    K = 3
+    lat = x[:K].cuda()
+    xin = torch.cat([lat, lat])
+    ar = torch.arange(K, device="cuda")
+    src = torch.cat([ar, ar])
+    net, cn = TGUNet(sd), TGControlNet(OC.synth_state_dict(4321))
+    t_dev = torch.full((6,), 321.0, dtype=torch.float32, device="cuda")
+    scale = torch.full((6,), 0.3, dtype=torch.float32, device="cuda")
+    g = torch.Generator().manual_seed(5)
+    cond = torch.rand(1, 3, 512, 512, generator=g).half().cuda()
+    ctx_text = torch.randn(2, 77, 768, generator=g).half().cuda()
+    emb = cn.embed_condition(cond)
+
+    def run(shared, control):
+        kw = {}
+        if shared:
+            kw["unique"] = (lat, src, ar)
+        if control:  # a stage-2 pair in batch rows 2..3 (uncond / cond of different trajectories here: no prefix sharing)
+            kw.update(controlnet=cn, control=dict(rows=(2, 4), ctx=ctx_text, cond_emb=emb))
+        return net.forward_raw(xin, t_dev, ctx.cuda(), ip_scale=scale, **kw)
+
+    for shared, control, sites in [(False, False, 31), (True, True, 31 + 11)]:  # the 64x64 and 32x32 levels (_STATS_MIN_HW)
+        ops.GN_CHECK_LOG = []
+        try:
+            a = run(shared, control)
+        finally:
+            log, ops.GN_CHECK_LOG = ops.GN_CHECK_LOG, None
+        assert len(log) == sites, len(log)
+        worst = max(log, key=lambda r: r[-1])
+        print("GroupNorm sites", len(log), "worst", worst)
+        assert worst[-1] <= 4e-3, worst
+        assert torch.equal(a, run(shared, control)), "not bit-reproducible"
+        os.environ["TG_GN_STATS"] = "0"
+        try:
+            b = run(shared, control)
+        finally:
+            del os.environ["TG_GN_STATS"]
+        assert (a.float() - b.float()).abs().max().item() <= 1e-2  # 1-ulp differences at 31 sites, propagated to eps

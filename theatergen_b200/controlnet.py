@@ -137,6 +137,14 @@ class TGControlNet(_BlockNet):
         B, _, H, W = sample.shape
         T = ctx.shape[1]
         temb_all, ctxkv = self._time_and_context(t_dev, ctx.contiguous(), B, ctxkv)  # ctxkv: project_context(ctx), optional
+        self._stats_begin(B)  # GroupNorm totals from the producers' epilogues (unet._BlockNet); zeroed on this stream
+        try:
+            return self._encode_blocks(sample, temb_all, ctxkv, cond_emb, share, B, H, W, T)
+        finally:
+            self._stats_end()
+
+    def _encode_blocks(self, sample, temb_all, ctxkv, cond_emb, share, B, H, W, T):
+        w = self.w
 
         def tf(p, x, h_, w_, share=None):
             return self._transformer(p, x, ctxkv, B, h_, w_, T, 0, None, None, None, False, None, share=share)
@@ -149,6 +157,7 @@ class TGControlNet(_BlockNet):
             src, first = share
             U = first.numel()
             assert B == 2 * U and n in (1, U), "shared prefix expects rows [uncond K | cond K] and one hint per trajectory"
+            # (conv_in's output is rewritten in place by the hint add: no epilogue totals, its GroupNorm measures itself)
             x = ops.conv_in_gemm(sample[:U].contiguous(), w["conv_in.w"], w["conv_in.b"])
             for b in range(U):
                 ops.add_inplace(x.view(-1)[b * per:(b + 1) * per], cond_emb[b % n].reshape(-1))
@@ -162,17 +171,25 @@ class TGControlNet(_BlockNet):
         x = self._mid(x, temb_all, tf, B, h_, w_)
         return skips, x
 
-    def add_residuals_inplace(self, ctrl, unet_skips, unet_mid, r0, r1):
+    def add_residuals_inplace(self, ctrl, unet_skips, unet_mid, r0, r1, take=None):
         """unet_skips[i][r0:r1] += zero_conv_i(skip_i);  unet_mid[r0:r1] += zero_conv_mid(mid)   (conditioning scale
-        1.0, the only value the reference uses: SURVEY.md A.3 #6).  One GEMM each, the addition is its epilogue."""
+        1.0, the only value the reference uses: SURVEY.md A.3 #6).  One GEMM each, the addition is its epilogue.
+        take: the UNet's statistics allocator -- a tensor that carries GroupNorm totals gets fresh ones for its rewritten
+        rows from the same epilogue (ops.GnStats.alt)."""
         w = self.w
         skips, mid = ctrl
-        for i, (s, u) in enumerate(zip(skips, unet_skips)):
-            C = s.shape[-1]
+
+        def add(src, u, wk, bk):
+            C = src.shape[-1]
             dst = u[r0:r1].view(-1, C)
-            ops.gemm(s.view(-1, C), w[f"zc{i}.w"], w[f"zc{i}.b"], residual=dst, out=dst)
-        dst = unet_mid[r0:r1].view(-1, 1280)
-        ops.gemm(mid.view(-1, 1280), w["zcm.w"], w["zcm.b"], residual=dst, out=dst)
+            st = getattr(u, "_gn", None)
+            alt = take(r1 - r0, C, u.shape[1] * u.shape[2]) if (st is not None and take is not None) else None
+            ops.gemm(src.view(-1, C), w[wk], w[bk], residual=dst, out=dst, stats=alt)
+            u._gn = None if alt is None else ops.GnStats(st.main, alt, r0, r1)
+
+        for i, (s, u) in enumerate(zip(skips, unet_skips)):
+            add(s, u, f"zc{i}.w", f"zc{i}.b")
+        add(mid, unet_mid, "zcm.w", "zcm.b")
 
     # the diffusers call surface (models/pipelines.py:770-778)
     def __call__(self, sample, timestep, encoder_hidden_states=None, controlnet_cond=None, conditioning_scale=1.0,

@@ -15,6 +15,22 @@ int tg_version(void) { return 100; }
 unsigned long long tg_launch_count(void) { return tg::g_launch_count; }
 int tg_init(void) { return tg::gemm_init(); }
 
+// one-shot GroupNorm-statistics target of the next tg_gemm / tg_conv3x3* call of this host thread
+static thread_local long long* t_stats = nullptr;
+static thread_local int t_stats_hw = 0;
+int tg_gemm_set_stats(long long* stats, int rows_per_image) {
+  TG_CHECK(stats == nullptr || rows_per_image > 0, "tg_gemm_set_stats: rows_per_image must be positive");
+  t_stats = stats;
+  t_stats_hw = rows_per_image;
+  return 0;
+}
+static void take_stats(tg::EpilogueSpec& e) {
+  e.stats = t_stats;
+  e.stats_hw = t_stats_hw;
+  t_stats = nullptr;
+  t_stats_hw = 0;
+}
+
 int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, const tg_half* Wt, int M, int N,
             int K, const tg_half* bias, const tg_half* rowbias, int rows_per_image, int rowbias_ld,
             const tg_half* residual, int ldr, int act, float out_scale, tg_half* out, int ldc, void* stream) {
@@ -22,6 +38,7 @@ int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, co
   tg::EpilogueSpec e;
   e.bias = H(bias); e.rowbias = H(rowbias); e.rows_per_image = rows_per_image; e.rowbias_ld = rowbias_ld;
   e.residual = H(residual); e.ldr = ldr; e.act = act; e.out_scale = out_scale;
+  take_stats(e);
   return tg::gemm_linear(H(A1), lda1, K1, H(A2), lda2, H(Wt), M, N, K, e, HM(out), ldc, ST(stream));
 }
 
@@ -33,6 +50,7 @@ int tg_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* W
   tg::EpilogueSpec e;
   e.bias = H(bias); e.rowbias = H(rowbias); e.rows_per_image = Hh * W; e.rowbias_ld = rowbias_ld;
   e.residual = H(residual); e.ldr = ldr; e.act = act; e.out_scale = out_scale;
+  take_stats(e);
   return tg::conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, e, HM(out), ldc, ST(stream));
 }
 
@@ -43,6 +61,7 @@ int tg_conv3x3_s2(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half
   TG_CHECK(act == 0 || act == 1, "tg_conv3x3_s2: act must be none / silu");
   tg::EpilogueSpec e;
   e.bias = H(bias); e.act = act;
+  take_stats(e);
   return tg::conv3x3_s2_nhwc(H(X), B, Hh, W, Cin, H(Wt), Cout, pad_lo, e, HM(out), ldc, ST(stream));
 }
 
@@ -51,6 +70,7 @@ int tg_upsample2x_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const
   TG_CHECK(X && Wt4 && out, "tg_upsample2x_conv3x3: null pointer");
   tg::EpilogueSpec e;
   e.bias = H(bias);
+  take_stats(e);
   return tg::upsample2x_conv3x3_nhwc(H(X), B, Hh, W, Cin, H(Wt4), Cout, e, HM(out), ST(stream));
 }
 
@@ -80,6 +100,14 @@ int tg_attn_set_prof(void* dev_buf) {
 int tg_gemm_set_prof(void* dev_buf) {
   tg::gemm_set_prof(static_cast<long long*>(dev_buf));
   return 0;
+}
+
+int tg_groupnorm_apply(const tg_half* x1, int C1, const long long* stats1, const long long* stats1_alt, const tg_half* x2, int C2,
+                       const long long* stats2, const long long* stats2_alt, int alt_b0, int alt_b1, int B, int HW,
+                       const tg_half* gamma, const tg_half* beta, float eps, int silu, tg_half* out, void* stream) {
+  TG_CHECK(x1 && gamma && beta && out && (C2 == 0 || x2), "tg_groupnorm_apply: null pointer");
+  return tg::groupnorm_apply_nhwc(H(x1), C1, stats1, stats1_alt, H(x2), C2, stats2, stats2_alt, alt_b0, alt_b1, B, HW, H(gamma),
+                                  H(beta), eps, silu, HM(out), ST(stream));
 }
 
 int tg_groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused) {

@@ -67,6 +67,9 @@ struct GemmArgs {
   int patch_bytes, ky_stride;  // KY3 convolution: bytes of the (box_h + 2)-row input patch, bytes of one image row in it
   float* ws;   // split-K partials: [tile][split][BN/4][128][4] fp32
   int* sem;    // split-K arrival counters, one per tile (self-resetting)
+  // GroupNorm statistics of the stored tile (EpilogueSpec::stats): [M / stats_hw][n_out / 2][2] fixed-point (sum, sumsq)
+  unsigned long long* stats;
+  int stats_hw;
   long long* prof;  // measurement only (tg_gemm_set_prof): per CTA {total, producer wait, MMA wait full, MMA wait acc, epilogue wait} cycles
 };
 
@@ -238,6 +241,30 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, float (&v)[32], 
     for (int j = 0; j < 4; ++j)
       h[j] = __floats2half2_rn(v[i * 8 + j * 2] * g.out_scale, v[i * 8 + j * 2 + 1] * g.out_scale);
     *reinterpret_cast<uint4*>(stage_row + ((i ^ ((row_in_warp >> 1) & 3)) << 4)) = o;
+  }
+}
+
+// GroupNorm statistics of the chunk AS STORED (fp16-rounded values read back from the staging buffer): per (image, channel
+// pair) the sum and the sum of squares over the warp's 32 rows x 2 columns, added to stats[image][pair] in 2^-24 fixed
+// point with 64-bit integer atomics.  Integer addition is associative, so the totals do not depend on the order the CTAs
+// arrive in: bit-reproducible, which float atomics would not be.  Lane (h, p): rows h, h+2, .. of column pair p -- the two
+// half-warps read different rows (different bank halves), conflict-free.  The consumer is norm.cu::gn_apply_pre_kernel.
+__device__ __forceinline__ void chunk_stats(const GemmArgs& g, const uint8_t* buf, int m_first, int n, int n_total, int lane) {
+  const int p = lane & 15, h = lane >> 4;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int r = h; r < 32; r += 2) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(buf + r * 64 + (((p >> 2) ^ ((r >> 1) & 3)) << 4) + ((p & 3) << 2));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    s += f.x + f.y;
+    q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  q += __shfl_xor_sync(0xffffffffu, q, 16);
+  if (h == 0) {
+    unsigned long long* dst = g.stats + ((size_t)(m_first / g.stats_hw) * (n_total >> 1) + ((n >> 1) + p)) * 2;
+    atomicAdd(dst, (unsigned long long)__float2ll_rn(s * 16777216.f));
+    atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(q * 16777216.f));
   }
 }
 
@@ -603,6 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             store_chunk(&tmC, buf, n0 + c, m0 + q * 32, g.out3d_w);
             bulk_commit();
           }
+          if (g.stats && m0 + q * 32 < g.M) chunk_stats(g, buf, m0 + q * 32, n0 + c, g.N, lane);
         }
         continue;
       }
@@ -669,6 +697,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           store_chunk(&tmC, buf, n_out, m0 + q * 32, g.out3d_w);  // rows >= M are clipped by the tensor map
           bulk_commit();
         }
+        if (g.stats && m0 + q * 32 < g.M) chunk_stats(g, buf, m0 + q * 32, n_out, g.N, lane);
       }
       // all TMEM reads of this accumulator are complete (tcgen05.wait::ld above): hand it back to the MMA warp
       tc_fence_before();
@@ -881,6 +910,9 @@ static void pick_tile(int M, int N, int K, int act, int conv, int patch_bytes, i
 static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, const __half* Wt, __half* out, int ldc,
                     cudaStream_t st) {
   if (g.act == 2) TG_CHECK(g.N % 128 == 0 && g.bias != nullptr, "geglu epilogue needs N%%128==0 and a bias");
+  if (g.stats)
+    TG_CHECK(g.act != 2 && g.stats_hw > 0 && g.stats_hw % 32 == 0 && g.M % g.stats_hw == 0,
+             "GroupNorm statistics epilogue: rows per image %d must be a multiple of 32 dividing M=%d (no GEGLU)", g.stats_hw, g.M);
   DeviceScratch* sc;
   if (get_scratch(&sc)) return -1;
   const int n_out = g.act == 2 ? g.N / 2 : g.N;
@@ -945,6 +977,8 @@ static void fill_args(GemmArgs& g, const EpilogueSpec& e) {
   g.ldr = e.ldr;
   g.act = e.act;
   g.out_scale = e.out_scale;
+  g.stats = reinterpret_cast<unsigned long long*>(e.stats);
+  g.stats_hw = e.stats_hw;
 }
 
 int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, const __half* Wt, int M, int N,

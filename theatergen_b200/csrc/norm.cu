@@ -331,6 +331,105 @@ gn_apply_kernel(const __half* __restrict__ x1, int C1, const __half* __restrict_
     *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(*reinterpret_cast<const uint4*>(src + (size_t)r * ld), sa, sb, silu);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// GroupNorm whose statistics came out of the producers' epilogues (gemm.cu::chunk_stats): per (image, channel pair) fixed-
+// point (sum, sumsq) totals.  Each CTA folds them to the 32 (mean, rstd) of its image (exact integer sums, moments in
+// double), then streams its slab like gn_apply_kernel: the activation is read ONCE and written once -- the statistics
+// pass over the tensor is gone.  An input may take the rows [b0, b1) of its statistics from a second block (`alt`, indexed
+// from b0): the rows the stage-2 ControlNet residuals were added to afterwards, by a GEMM that produced fresh totals.
+// ---------------------------------------------------------------------------------------------------------
+struct GnStatsSrc {
+  const long long* main;  // [B][C/2][2]
+  const long long* alt;   // [b1 - b0][C/2][2] or null
+  int b0, b1;
+};
+__device__ __forceinline__ const long long* gn_src_of(const GnStatsSrc& s, int b, int C) {
+  return (s.alt != nullptr && b >= s.b0 && b < s.b1) ? s.alt + (size_t)(b - s.b0) * C : s.main + (size_t)b * C;
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_pre_kernel(const __half* __restrict__ x1, int C1, GnStatsSrc s1, const __half* __restrict__ x2, int C2, GnStatsSrc s2,
+                    int HW, int slabs, const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
+                    __half* __restrict__ out) {
+  __shared__ float s_stat[2 * GN_GROUPS];
+  __shared__ long long s_tot[2 * (GN_THREADS * 8 / 2)];  // (sum, sumsq) per channel pair, C <= 2560
+  grid_dep_launch();
+  grid_dep_wait();
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int C = C1 + C2, cpg = C / GN_GROUPS, c8n = C / 8;
+  {
+    // one L2 round trip: every pair's totals are fetched in parallel, then 64 threads (group, sum | sumsq) fold their pairs
+    const long long* p1 = gn_src_of(s1, b, C1);
+    const long long* p2 = C2 ? gn_src_of(s2, b, C2) : nullptr;
+    for (int k = threadIdx.x; k < C / 2; k += GN_THREADS) {
+      const int c = 2 * k;
+      const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(c < C1 ? p1 + c : p2 + (c - C1)));
+      s_tot[2 * k] = v.x;
+      s_tot[2 * k + 1] = v.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * GN_GROUPS) {
+      const int g = threadIdx.x >> 1, which = threadIdx.x & 1, ppg = cpg >> 1;
+      long long a = 0;
+      for (int k = 0; k < ppg; ++k) a += s_tot[2 * (g * ppg + k) + which];
+      const double n = (double)HW * cpg;
+      const double m1 = (double)a * (1.0 / 16777216.0) / n;  // mean (which = 0) or E[x^2] (which = 1)
+      const double other = __shfl_xor_sync(0xffffffffu, m1, 1);
+      if (which == 0) {
+        s_stat[2 * g] = (float)m1;
+        s_stat[2 * g + 1] = rsqrtf((float)fmax(other - m1 * m1, 0.0) + eps);
+      }
+    }
+  }
+  __syncthreads();
+  const int R = GN_THREADS / c8n;
+  const int chunk = threadIdx.x % c8n, rl = threadIdx.x / c8n;
+  if (rl >= R) return;
+  const int c = chunk * 8;
+  float sa[8], sb[8];
+  gn_scale_shift(s_stat, gamma, beta, c, cpg, sa, sb);
+  const __half* src;
+  int ld;
+  if (c < C1) { src = x1 + c; ld = C1; } else { src = x2 + (c - C1); ld = C2; }
+  src += (size_t)b * HW * ld;
+  __half* dst = out + (size_t)b * HW * C + c;
+  const int rows_per = (HW + slabs - 1) / slabs;
+  const int r0 = slab * rows_per, r1 = min(HW, r0 + rows_per);
+  int r = r0 + rl;
+  for (; r + 3 * R < r1; r += 4 * R) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(r + u * R) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) *reinterpret_cast<uint4*>(dst + (size_t)(r + u * R) * C) = gn_emit(v[u], sa, sb, silu);
+  }
+  for (; r < r1; r += R)
+    *reinterpret_cast<uint4*>(dst + (size_t)r * C) = gn_emit(*reinterpret_cast<const uint4*>(src + (size_t)r * ld), sa, sb, silu);
+}
+
+int groupnorm_apply_nhwc(const __half* x1, int C1, const long long* st1, const long long* st1_alt, const __half* x2, int C2,
+                         const long long* st2, const long long* st2_alt, int alt_b0, int alt_b1, int B, int HW,
+                         const __half* gamma, const __half* beta, float eps, int silu, __half* out, cudaStream_t st) {
+  const int C = C1 + C2;
+  TG_CHECK(C % (2 * GN_GROUPS) == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C / 8 <= GN_THREADS, "groupnorm_apply: C1=%d C2=%d unsupported", C1, C2);
+  TG_CHECK(st1 != nullptr && (C2 == 0 || st2 != nullptr), "groupnorm_apply: statistics missing");
+  const int R = GN_THREADS / (C / 8);
+  static int per_sm = -1;  // CTAs per SM the grid is sized for (TG_GN_PRE_PER_SM: tools/gn_stats_bench.py sweeps it)
+  if (per_sm < 0) {
+    const char* e = getenv("TG_GN_PRE_PER_SM");
+    per_sm = e ? atoi(e) : 3;  // measured best at every level (B = 10)
+    if (per_sm < 1) per_sm = 1;
+  }
+  int aslabs = (per_sm * 148) / B;
+  aslabs = max(1, min(aslabs, HW / max(1, 4 * R)));
+  GnStatsSrc s1{st1, st1_alt, alt_b0, alt_b1}, s2{st2, st2_alt, alt_b0, alt_b1};
+  TG_CUDA(launch_kernel(gn_apply_pre_kernel, dim3(aslabs, B), dim3(GN_THREADS), 0, st, 1, x1, C1, s1, x2, C2, s2, HW, aslabs, gamma,
+                        beta, eps, silu, out));
+  TG_COUNT_LAUNCH();
+  TG_LAUNCH_CHECK();
+  return 0;
+}
+
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st) {
   const int C = C1 + C2;

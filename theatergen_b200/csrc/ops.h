@@ -14,6 +14,10 @@ struct EpilogueSpec {
   int ldr = 0;
   int act = 0;                       // 0 none, 1 SiLU, 2 GEGLU (packed weight layout)
   float out_scale = 1.f;
+  // optional GroupNorm statistics of the stored output, accumulated by the epilogue (api: tg_gemm_set_stats):
+  // stats[image = row / stats_hw][column pair][2] += 2^24 x (sum, sum of squares) as 64-bit integers; zeroed by the caller
+  long long* stats = nullptr;
+  int stats_hw = 0;
 };
 
 // out[M,N] = epi( [A1 | A2][M,K] * Wt[N,K]^T )
@@ -45,6 +49,10 @@ void attn_cross_set_impl(int mode);
 // workspace: >= B*64*32*2 floats.
 int groupnorm_nhwc(const __half* x1, int C1, const __half* x2, int C2, int B, int HW, const __half* gamma,
                    const __half* beta, float eps, int silu, __half* out, float* workspace, cudaStream_t st);
+// the same normalisation from statistics accumulated by the producing GEMMs' epilogues (EpilogueSpec::stats): one pass
+int groupnorm_apply_nhwc(const __half* x1, int C1, const long long* st1, const long long* st1_alt, const __half* x2, int C2,
+                         const long long* st2, const long long* st2_alt, int alt_b0, int alt_b1, int B, int HW,
+                         const __half* gamma, const __half* beta, float eps, int silu, __half* out, cudaStream_t st);
 // launch-geometry knobs of groupnorm_nhwc (<= 0 / < 0 keep the current value); used by tools/gn_bench.py
 void groupnorm_tune(int stats_slabs, int apply_ctas_per_sm, int fused);
 int layernorm_rows(const __half* x, int ldx, const __half* gamma, const __half* beta, float eps, __half* out,

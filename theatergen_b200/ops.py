@@ -72,9 +72,30 @@ def _chk16(*ts):
             assert t.is_cuda and t.dtype == torch.float16 and t.stride(-1) == 1, (t.dtype, t.stride(), t.device)
 
 
+class GnStats:
+    """GroupNorm totals of a tensor, accumulated by the epilogue of the GEMM that produced it (tg_gemm_set_stats):
+    `main` int64 [images, C/2, 2]; images [b0, b1) read `alt` [b1-b0, C/2, 2] instead (rows re-measured by the in-place
+    ControlNet residual GEMM)."""
+    __slots__ = ("main", "alt", "b0", "b1")
+
+    def __init__(self, main, alt=None, b0=0, b1=0):
+        self.main, self.alt, self.b0, self.b1 = main, alt, b0, b1
+
+
+def _arm_stats(stats, M):
+    """Arms the next tg_gemm / tg_conv3x3* launch of this thread to add its output's GroupNorm totals to `stats`
+    (zeroed int64 [images, N/2, 2])."""
+    if stats is None:
+        return
+    assert stats.is_cuda and stats.dtype == torch.int64 and stats.is_contiguous() and stats.dim() == 3 and stats.shape[2] == 2
+    assert M % stats.shape[0] == 0, (M, stats.shape)
+    _lib.check(_lib.lib().tg_gemm_set_stats(stats.data_ptr(), M // stats.shape[0]), "tg_gemm_set_stats")
+
+
 def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=None, act=TG_ACT_NONE,
-         out_scale=1.0, out=None):
-    """out[M,N] = act([a|a2] @ w.T + bias + rowbias[row // rows_per_image]) + residual ; w is [N,K]."""
+         out_scale=1.0, out=None, stats=None):
+    """out[M,N] = act([a|a2] @ w.T + bias + rowbias[row // rows_per_image]) + residual ; w is [N,K].
+    stats: see _arm_stats."""
     _chk16(a, w, bias, a2, rowbias, residual, out)
     assert w.is_contiguous(), "gemm: the weight operand must be a dense [N,K] matrix"
     M, K1 = a.shape
@@ -86,6 +107,7 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
     n_out = N // 2 if act == TG_ACT_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
+    _arm_stats(stats, M)
     rc = _timed("gemm_tc_kernel", 2.0 * M * N * K, 2.0 * (M * K + N * K + M * n_out + (M * N if residual is not None else 0)),
                 lambda: _lib.lib().tg_gemm(_p(a), a.stride(0), K1, _p(a2), 0 if a2 is None else a2.stride(0), _p(w), M, N, K,
                             _p(bias), _p(rowbias), rows_per_image, 0 if rowbias is None else rowbias.stride(0),
@@ -95,7 +117,7 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
     return out
 
 
-def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, out_scale=1.0, out=None):
+def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, out_scale=1.0, out=None, stats=None):
     """x [B,H,W,Cin] NHWC, w [Cout,3,3,Cin] -> [B,H,W,Cout] (pad 1, stride 1)."""
     _chk16(x, w, bias, rowbias, residual, out)
     B, H, W, Cin = x.shape
@@ -105,6 +127,7 @@ def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, ou
         out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=x.device)
     res2 = None if residual is None else residual.reshape(B * H * W, -1)
     Mc = B * H * W
+    _arm_stats(stats, Mc)
     rc = _timed("gemm_tc_kernel", 2.0 * Mc * Cout * 9 * Cin,
                 2.0 * (Mc * Cin + Cout * 9 * Cin + Mc * Cout + (Mc * Cout if res2 is not None else 0)),
                 lambda: _lib.lib().tg_conv3x3(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), _p(rowbias),
@@ -128,14 +151,35 @@ def _gn_workspace(device, B):
     return ws
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=False, out=None, workspace=None):
-    """GroupNorm(32)(+SiLU) over channels-last [B,HW,C1] (| x2 [B,HW,C2]) -> [B,HW,C1+C2]."""
+GN_CHECK_LOG = None  # tests: a list here makes every statistics-fed groupnorm() also run the two-pass kernels and log the gap
+
+
+def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=False, out=None, workspace=None, st1=None, st2=None):
+    """GroupNorm(32)(+SiLU) over channels-last [B,HW,C1] (| x2 [B,HW,C2]) -> [B,HW,C1+C2].
+    st1 / st2 (GnStats): totals the producers of x1 / x2 accumulated in their epilogues -> one pass (tg_groupnorm_apply);
+    without them the statistics are computed here (tg_groupnorm)."""
     _chk16(x1, x2, gamma, beta, out)
     B, HW, C1 = x1.shape
     C2 = 0 if x2 is None else x2.shape[-1]
     assert x1.is_contiguous() and (x2 is None or x2.is_contiguous())
     if out is None:
         out = torch.empty((B, HW, C1 + C2), dtype=torch.float16, device=x1.device)
+    if st1 is not None and (x2 is None or st2 is not None):
+        assert st1.main.shape == (B, C1 // 2, 2) and (st2 is None or st2.main.shape == (B, C2 // 2, 2))
+        alts = [s for s in (st1, st2) if s is not None and s.alt is not None]
+        b0, b1 = (alts[0].b0, alts[0].b1) if alts else (0, 0)
+        assert all((s.b0, s.b1) == (b0, b1) for s in alts)
+        rc = _timed("groupnorm", 0, 2.0 * 2 * B * HW * (C1 + C2),
+                    lambda: _lib.lib().tg_groupnorm_apply(_p(x1), C1, _p(st1.main), _p(st1.alt), _p(x2), C2,
+                                                          _p(None if st2 is None else st2.main),
+                                                          _p(None if st2 is None else st2.alt), b0, b1, B, HW, _p(gamma),
+                                                          _p(beta), float(eps), int(silu), _p(out), _stream()),
+                    tag=f"gn-apply B={B} HW={HW} C={C1 + C2}")
+        _lib.check(rc, "tg_groupnorm_apply")
+        if GN_CHECK_LOG is not None:
+            ref = groupnorm(x1, gamma, beta, eps, x2=x2, silu=silu)
+            GN_CHECK_LOG.append((B, HW, C1, C2, (out.float() - ref.float()).abs().max().item()))
+        return out
     ws = workspace if workspace is not None else _gn_workspace(x1.device, B)
     rc = _timed("groupnorm", 0, 2.0 * 3 * B * HW * (C1 + C2),
                 lambda: _lib.lib().tg_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, _p(gamma), _p(beta), float(eps), int(silu),
@@ -209,7 +253,7 @@ def attention_cross_ip(q, kt, vt, ki, vi, B, heads, n_text, n_ip, ip_scale=None,
     return out
 
 
-def conv3x3_s2(x, w, bias=None, *, pad_lo=1, act=TG_ACT_NONE, out=None):
+def conv3x3_s2(x, w, bias=None, *, pad_lo=1, act=TG_ACT_NONE, out=None, stats=None):
     """x [B,H,W,Cin] NHWC, w [Cout,3,3,Cin] -> [B,H/2,W/2,Cout]: 3x3 convolution with stride 2 (diffusers Downsample2D) as an
     implicit GEMM whose TMA gathers every other pixel -- no im2col buffer.  pad_lo=1: padding 1; pad_lo=0: the VAE encoder's
     (0, 1) padding."""
@@ -220,6 +264,7 @@ def conv3x3_s2(x, w, bias=None, *, pad_lo=1, act=TG_ACT_NONE, out=None):
     if out is None:
         out = torch.empty((B, H // 2, W // 2, Cout), dtype=torch.float16, device=x.device)
     Mc = B * (H // 2) * (W // 2)
+    _arm_stats(stats, Mc)
     rc = _timed("gemm_tc_kernel", 2.0 * Mc * Cout * 9 * Cin, 2.0 * (B * H * W * Cin + Cout * 9 * Cin + Mc * Cout),
                 lambda: _lib.lib().tg_conv3x3_s2(_p(x), B, H, W, Cin, _p(w), Cout, _p(bias), int(pad_lo), act, _p(out), Cout,
                                                  _stream()),
@@ -228,7 +273,7 @@ def conv3x3_s2(x, w, bias=None, *, pad_lo=1, act=TG_ACT_NONE, out=None):
     return out
 
 
-def upsample2x_conv3x3(x, w4, bias=None, out=None):
+def upsample2x_conv3x3(x, w4, bias=None, out=None, stats=None):
     """x [B,H,W,Cin] NHWC, w4 = weights.pack_upsample_conv3x3(w) [4,Cout,2,2,Cin] -> [B,2H,2W,Cout] = conv3x3(nearest_x2(x)):
     four 2x2 convolutions on the low-resolution grid (2.25x fewer MACs, no upsampled tensor)."""
     _chk16(x, w4, bias, out)
@@ -238,6 +283,7 @@ def upsample2x_conv3x3(x, w4, bias=None, out=None):
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.float16, device=x.device)
     Mc = B * H * W
+    _arm_stats(stats, Mc)  # each of the four phase GEMMs covers H*W rows of every image
     rc = _timed("gemm_tc_kernel", 2.0 * 4 * Mc * Cout * 4 * Cin, 2.0 * (Mc * Cin + 16 * Cout * Cin + 4 * Mc * Cout),
                 lambda: _lib.lib().tg_upsample2x_conv3x3(_p(x), B, H, W, Cin, _p(w4), Cout, _p(bias), _p(out), _stream()),
                 tag=f"upconv M={4 * Mc} N={Cout} K={4 * Cin} B={B} H={2 * H} W={2 * W}")
@@ -320,7 +366,7 @@ def pack_conv_in(w):
     return wp
 
 
-def conv_in_gemm(x_nchw, w_packed, bias, silu=False, out=None):
+def conv_in_gemm(x_nchw, w_packed, bias, silu=False, out=None, stats=None):
     """3x3 / pad 1 convolution of a small-channel NCHW image as im2col (K padded to 64) + tensor-core GEMM
     -> NHWC [B,H,W,Cout]."""
     _chk16(x_nchw, w_packed, bias, out)
@@ -330,7 +376,7 @@ def conv_in_gemm(x_nchw, w_packed, bias, silu=False, out=None):
     _lib.check(_lib.lib().tg_im2col_small(_p(x_nchw), _p(cols), B, Cin, H, W, _stream()), "tg_im2col_small")
     Cout = w_packed.shape[0]
     y = gemm(cols, w_packed, bias, act=TG_ACT_SILU if silu else TG_ACT_NONE,
-             out=None if out is None else out.view(B * H * W, Cout))
+             out=None if out is None else out.view(B * H * W, Cout), stats=stats)
     return y.view(B, H, W, Cout)
 
 

@@ -141,27 +141,78 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
     return t, rows
 
 
-def downsample_conv(x, w9, bias, cout, pad_lo=1, act=ops.TG_ACT_NONE):
+def downsample_conv(x, w9, bias, cout, pad_lo=1, act=ops.TG_ACT_NONE, stats=None):
     """diffusers Downsample2D: 3x3 convolution, stride 2.  w9 = packed weight [Cout, 9*Cin] (the [Cout,3,3,Cin] tensor flattened).
     Default: implicit GEMM with a stride-2 TMA gather; TG_CONV_S2=0 selects the im2col buffer + GEMM of round 1 (A/B)."""
     B, H, W, cin = x.shape
     if os.environ.get("TG_CONV_S2", "1") != "0":
-        return ops.conv3x3_s2(x, w9.view(cout, 3, 3, cin), bias, pad_lo=pad_lo, act=act)
-    return ops.gemm(ops.im2col_s2(x, pad_lo=pad_lo), w9, bias, act=act).view(B, H // 2, W // 2, cout)
+        return _set(ops.conv3x3_s2(x, w9.view(cout, 3, 3, cin), bias, pad_lo=pad_lo, act=act, stats=stats), stats)
+    return _set(ops.gemm(ops.im2col_s2(x, pad_lo=pad_lo), w9, bias, act=act, stats=stats).view(B, H // 2, W // 2, cout), stats)
 
 
-def upsample_conv(x, w, name):
+def upsample_conv(x, w, name, stats=None):
     """diffusers Upsample2D: nearest x2 + 3x3 convolution.  Default: four 2x2 convolutions on the low-resolution grid
     (w[name + ".w4"], weights.pack_upsample_conv3x3); TG_UPCONV=0 selects upsample kernel + 3x3 convolution (A/B)."""
     if os.environ.get("TG_UPCONV", "1") != "0":
-        return ops.upsample2x_conv3x3(x, w[name + ".w4"], w[name + ".b"])
-    return ops.conv3x3(ops.upsample2x(x), w[name + ".w"], w[name + ".b"])
+        return _set(ops.upsample2x_conv3x3(x, w[name + ".w4"], w[name + ".b"], stats=stats), stats)
+    return _set(ops.conv3x3(ops.upsample2x(x), w[name + ".w"], w[name + ".b"], stats=stats), stats)
+
+
+def _st(x):
+    """GroupNorm totals travelling with a tensor (set by its producer through _set), or None."""
+    return None if x is None else getattr(x, "_gn", None)
+
+
+def _set(x, stats):
+    if stats is not None:
+        x._gn = ops.GnStats(stats)
+    return x
 
 
 class _BlockNet:
     """Execution of the blocks the UNet and the ControlNet share (ResnetBlock2D, Transformer2DModel, the time
-    embedding and the encoder half), on packed weights held in self.w / self.resnets / self.transformers."""
+    embedding and the encoder half), on packed weights held in self.w / self.resnets / self.transformers.
+
+    GroupNorm statistics: every GroupNorm input of these networks is the output of a tensor-core GEMM / convolution, so
+    the producer's epilogue accumulates the per-image (sum, sum of squares) totals (ops.gemm(..., stats=)) and the
+    normalisation is ONE pass over the activation (ops.groupnorm(..., st1=, st2=)).  The totals of one forward live in an
+    arena (`_stats_begin` zeroes it, `_take` hands out blocks) and travel with the tensors as the attribute `_gn`; a tensor
+    without it (foreign input, TG_GN_STATS=0) takes the self-contained GroupNorm kernels."""
     dtype = torch.float16
+    _STATS_CHANNELS = 112 * 1024  # >= channels of all GroupNorm-feeding tensors of one forward (UNet: ~96 K)
+
+    def _stats_begin(self, B):
+        self._arena = None
+        if os.environ.get("TG_GN_STATS", "1") == "0":
+            return
+        arenas = self.__dict__.setdefault("_arenas", {})  # one per batch size, never freed: captured graphs point into them
+        a = arenas.get(B)
+        if a is None:
+            a = arenas[B] = [torch.zeros(B * self._STATS_CHANNELS, dtype=torch.int64, device=self.device), None]
+        else:
+            (a[0] if a[1] is None else a[0][:a[1]]).zero_()
+        self._arena, self._arena_off = a, 0
+
+    def _stats_end(self):
+        if getattr(self, "_arena", None) is not None:
+            self._arena[1] = max(self._arena[1] or 0, self._arena_off)
+        self._arena = None
+
+    _STATS_MIN_HW = 1024  # measured (tools/gn_stats_bench.py, B = 10): the one-pass norm wins at 64x64 and 32x32 (-7..-16 us per
+    #                       site); at 16x16 / 8x8 the cluster kernel (slab on chip) is as fast and the producers' epilogue
+    #                       work would be pure cost
+
+    def _take(self, images, C, hw):
+        """A zeroed [images, C/2, 2] block of this forward's arena for a tensor of `hw` pixels per image (None when the
+        statistics epilogues are off or the tensor's GroupNorm is better left to the self-measuring kernel)."""
+        a = getattr(self, "_arena", None)
+        if a is None or hw < self._STATS_MIN_HW:
+            return None
+        n = images * C
+        assert self._arena_off + n <= a[0].numel(), "GroupNorm statistics arena exhausted"
+        v = a[0][self._arena_off:self._arena_off + n].view(images, C // 2, 2)
+        self._arena_off += n
+        return v
 
     def project_context(self, ctx, out=None):
         """K / V projections of the context tokens for every cross-attention layer in one GEMM: [B, T, 768] ->
@@ -197,6 +248,8 @@ class _BlockNet:
             src, first = share
             U = x.shape[0]
             skips = [x.index_select(0, src)]
+            if _st(x) is not None:
+                _set(skips[0], _st(x).main.index_select(0, src))
             xu = self._resnet("down_blocks.0.resnets.0", x, None, temb_all.index_select(0, first), U, h_, w_)
             x = tf("down_blocks.0.attentions.0", xu, h_, w_, share=src)
             skips.append(x)
@@ -212,7 +265,7 @@ class _BlockNet:
                 skips.append(x)
             if i < 3:
                 c = BLOCK_OUT[i]
-                x = downsample_conv(x, w[f"down{i}.w"], w[f"down{i}.b"], c)
+                x = downsample_conv(x, w[f"down{i}.w"], w[f"down{i}.b"], c, stats=self._take(B, c, (h_ // 2) * (w_ // 2)))
                 h_, w_ = h_ // 2, w_ // 2
                 skips.append(x)
         return x, skips, h_, w_
@@ -228,17 +281,18 @@ class _BlockNet:
         cin, co = r["cin"], r["cout"]
         HW = H * W
         n1 = ops.groupnorm(x1.view(B, HW, -1), r["n1g"], r["n1b"], 1e-5, x2=None if x2 is None else x2.view(B, HW, -1),
-                           silu=True)
+                           silu=True, st1=_st(x1), st2=_st(x2))
+        sh, so = self._take(B, co, HW), self._take(B, co, HW)
         h = ops.conv3x3(n1.view(B, H, W, cin), r["c1w"], r["c1b"],
-                        rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co])
-        n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True)
+                        rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co], stats=sh)
+        n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True, st1=_st(_set(h, sh)))
         if "scw" in r:
             sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
             sc = sc.view(B, H, W, co)
         else:
             assert x2 is None
             sc = x1
-        return ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc)
+        return _set(ops.conv3x3(n2.view(B, H, W, co), r["c2w"], r["c2b"], residual=sc, stats=so), so)
 
     def _transformer(self, p, x, ctxkv, B, H, W, n_text, n_ip, ip_scale, capture, save_keys, cond_only, token_idx,
                      capture_b0=None, share=None):
@@ -247,7 +301,7 @@ class _BlockNet:
         t = self.transformers[p]
         Bu = x.shape[0] if share is not None else B   # rows the context-independent part runs on
         C, M, Mu = t["C"], B * H * W, Bu * H * W
-        n = ops.groupnorm(x.view(Bu, H * W, C), t["ng"], t["nb"], 1e-6, silu=False)
+        n = ops.groupnorm(x.view(Bu, H * W, C), t["ng"], t["nb"], 1e-6, silu=False, st1=_st(x))
         h = ops.gemm(n.view(Mu, C), t["piw"], t["pib"])
         # self attention
         ln = ops.layernorm(h, t["norm1g"], t["norm1b"])
@@ -284,7 +338,8 @@ class _BlockNet:
         ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
         ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
         h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
-        return ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C)).view(B, H, W, C)
+        so = self._take(B, C, H * W)
+        return _set(ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C), stats=so).view(B, H, W, C), so)
 
 
 class TGUNet(_BlockNet):
@@ -400,6 +455,17 @@ class TGUNet(_BlockNet):
         if n_ip and ip_scale is None:
             ip_scale = self._ip_scale_tensor(B)
         temb_all, ctxkv = self._time_and_context(t_dev, ctx, B, ctxkv)
+        self._stats_begin(B)
+        try:
+            return self._forward_blocks(sample, t_dev, temb_all, ctxkv, ip_scale, down_residuals, mid_residual, capture,
+                                        save_keys, cond_only, token_idx, capture_b0, controlnet, control, unique, n_text, n_ip)
+        finally:
+            self._stats_end()
+
+    def _forward_blocks(self, sample, t_dev, temb_all, ctxkv, ip_scale, down_residuals, mid_residual, capture, save_keys,
+                        cond_only, token_idx, capture_b0, controlnet, control, unique, n_text, n_ip):
+        w = self.w
+        B, _, H, W = sample.shape
 
         def tf(p, x, h_, w_, share=None):
             return self._transformer(p, x, ctxkv, B, h_, w_, n_text, n_ip, ip_scale, capture, save_keys, cond_only,
@@ -425,29 +491,32 @@ class TGUNet(_BlockNet):
                 finally:
                     _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
         if unique is not None:
-            x = ops.conv_in_gemm(unique[0], w["conv_in.w"], w["conv_in.b"])
+            s0 = self._take(unique[0].shape[0], 320, H * W)
+            x = _set(ops.conv_in_gemm(unique[0], w["conv_in.w"], w["conv_in.b"], stats=s0), s0)
             x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W, share=(unique[1], unique[2]))
         else:
-            x = ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"])
+            s0 = self._take(B, 320, H * W)
+            x = _set(ops.conv_in_gemm(sample, w["conv_in.w"], w["conv_in.b"], stats=s0), s0)
             x, skips, h_, w_ = self._encoder(x, temb_all, tf, B, H, W)
         if down_residuals is not None:  # ControlNet: new tensors, the mid-block input stays untouched
             skips = [ops.add_inplace(s.clone(), ops.nchw_to_nhwc(r)) for s, r in zip(skips, down_residuals)]
         x = self._mid(x, temb_all, tf, B, h_, w_)
         if mid_residual is not None:
             x = ops.add_inplace(x, ops.nchw_to_nhwc(mid_residual))
+            x._gn = None  # rewritten in place: the producer's totals no longer describe it
         if ctrl is not None:  # after the mid block: the last skip tensor is also the mid block's input
             if side is not None:
                 torch.cuda.current_stream().wait_stream(side)
-            controlnet.add_residuals_inplace(ctrl, skips, x, r0, r1)
+            controlnet.add_residuals_inplace(ctrl, skips, x, r0, r1, take=self._take)
         for i in range(4):
             for j in range(3):
                 x = self._resnet(f"up_blocks.{i}.resnets.{j}", x, skips.pop(), temb_all, B, h_, w_)
                 if i > 0:
                     x = tf(f"up_blocks.{i}.attentions.{j}", x, h_, w_)
             if i < 3:
-                x = upsample_conv(x, w, f"up{i}")
+                x = upsample_conv(x, w, f"up{i}", stats=self._take(B, x.shape[-1], 4 * h_ * w_))
                 h_, w_ = 2 * h_, 2 * w_
-        n = ops.groupnorm(x.view(B, h_ * w_, 320), w["no.g"], w["no.b"], 1e-5, silu=True)
+        n = ops.groupnorm(x.view(B, h_ * w_, 320), w["no.g"], w["no.b"], 1e-5, silu=True, st1=_st(x))
         return ops.conv_out_tc(n.view(B, h_, w_, 320), w["conv_out.w64"], w["conv_out.b64"], 4)
 
     # the reference call surface (ip_adapter/unet_2d_condition.py:799-813)
