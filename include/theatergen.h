@@ -144,7 +144,9 @@ int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, 
 
 /* Same contract on the tcgen05 path (TMA-fed tiles, S/O accumulators in TMEM) for head dims <= 64: Q/K/V must be
  * head-padded to 64 columns (head h at column h*64, columns [d,64) zero -- obtained for free by zero rows in the
- * fused QKV projection weight), Nq == Nk == N with N % 128 == 0.  O is written unpadded ([B*N, heads*d]). */
+ * fused QKV projection weight), Nq == Nk == N with N % 128 == 0.  O is written unpadded ([B*N, heads*d]).
+ * d <= 56: 64 columns per head; d <= 120: 128 columns per head; 128 <= d <= 176 (multiple of 16; SD-1.5's d = 160):
+ * heads PACKED (head h at column h*d, no padding) -- three 64-column chunks per head. */
 int tg_attention_tc(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
                     int ldo, int B, int heads, int N, int d, float scale, void* stream);
 

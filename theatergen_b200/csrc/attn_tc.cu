@@ -55,7 +55,8 @@ template <int CH>
 struct AttnCfg {
   static constexpr int KV_BYTES = CH * AT_CHUNK_BYTES;          // 128 keys of K (or V), CH chunks
   static constexpr int STAGE_BYTES = 2 * KV_BYTES;              // K chunks | V chunks
-  static constexpr int BAR_OFFSET = AT_STAGES * STAGE_BYTES;
+  static constexpr int STAGES = CH == 3 ? 2 : AT_STAGES;        // CH = 3: 96 KB per stage
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int SMEM = BAR_OFFSET + AT_NUM_BARS * 8 + 16 + 1024;
   // tensor memory columns, VAR 0: S0 | S1 (P_j overlays the first 32 columns of S_j) | O (64 per chunk) | Q (8 per K-step)
   //                        VAR 2: S0 | S1 | P (32) | O (64 per chunk) | Q (8 per K-step; 24 for d = 40 -> 248 of 256)
@@ -97,9 +98,10 @@ template <int CH, int VAR, bool PROF>
 __global__ void __launch_bounds__(AT_THREADS, CH == 1 ? 2 : 1)
 attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, __half* __restrict__ O, int ldo, int N, int d,
-               float scale_log2, long long* __restrict__ prof) {
+               float scale_log2, long long* __restrict__ prof, int hstride) {
+  // hstride: columns between consecutive heads in Q / K / V (CH * 64 for the zero-padded layouts, d for packed heads)
   using Cfg = AttnCfg<CH>;
-  constexpr int AT_KV_BYTES = Cfg::KV_BYTES, AT_STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int AT_KV_BYTES = Cfg::KV_BYTES, AT_STAGE_BYTES = Cfg::STAGE_BYTES, AT_STAGES = Cfg::STAGES;
   constexpr uint32_t AT_TS = Cfg::TS, AT_TO = VAR == 2 ? Cfg::TO2 : Cfg::TO, AT_TQ = VAR == 2 ? Cfg::TQ2 : Cfg::TQ;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -167,8 +169,8 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
         mbar_arrive_expect_tx(&kv_full[s], AT_STAGE_BYTES);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          tma_load_2d(dst + c * AT_CHUNK_BYTES, &tmK, &kv_full[s], (h * CH + c) * ATD, row_base + i * AT_TPS * ATK);
-          tma_load_2d(dst + AT_KV_BYTES + c * AT_CHUNK_BYTES, &tmV, &kv_full[s], (h * CH + c) * ATD, row_base + i * AT_TPS * ATK);
+          tma_load_2d(dst + c * AT_CHUNK_BYTES, &tmK, &kv_full[s], h * hstride + c * ATD, row_base + i * AT_TPS * ATK);
+          tma_load_2d(dst + AT_KV_BYTES + c * AT_CHUNK_BYTES, &tmV, &kv_full[s], h * hstride + c * ATD, row_base + i * AT_TPS * ATK);
         }
       }
     }
@@ -268,7 +270,7 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
 
     // Q row -> tensor memory (A operand of every S MMA): 16 fp16 = 8 packed columns per MMA K-step
     {
-      const uint4* qrow = reinterpret_cast<const uint4*>(Q + (size_t)(row_base + q0 + r) * ldq + h * CH * ATD);
+      const uint4* qrow = reinterpret_cast<const uint4*>(Q + (size_t)(row_base + q0 + r) * ldq + h * hstride);
       for (int k = 0; k < ksteps; ++k) {
         uint4 v[2];
         v[0] = __ldg(qrow + 2 * k);
@@ -866,7 +868,10 @@ static int launch_attn_tc_v(const __half* Q, const __half* K, const __half* V, i
   auto kern = attn_tc_kernel<CH, VAR, PROF>;
   TG_SMEM_ATTR_ONCE(kern, Cfg::SMEM);
   CUtensorMap tk, tv;
-  const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * CH * ATD;
+  // CH = 3 (d = 160): heads packed at stride d -- the 64-column boxes of a head's last chunk reach into the next head (or
+  // past the tensor: zero fill); those columns lie beyond the K extent of Q K^T and beyond the output columns that are read
+  const int hstride = CH == 3 ? d : CH * ATD;
+  const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * hstride;
   if (make_tmap_2d(&tk, K, rows, cols, ldk, AT_TPS * ATK)) return -1;
   if (make_tmap_2d(&tv, V, rows, cols, ldv, AT_TPS * ATK)) return -1;
   static int smem_pad = -1;  // TG_ATTN_ONE_CTA=1 (measurement): request > half of the SM's shared memory -> one CTA per SM
@@ -874,7 +879,7 @@ static int launch_attn_tc_v(const __half* Q, const __half* K, const __half* V, i
   const int smem = Cfg::SMEM > smem_pad ? Cfg::SMEM : smem_pad;
   if (smem_pad) TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   TG_CUDA(launch_kernel(kern, dim3(N / ATQ, heads, B), dim3(AT_THREADS), smem, st, 1, Q, ldq, tk, tv, O, ldo, N, d,
-                        scale * 1.4426950408889634f, PROF ? g_attn_prof : (long long*)nullptr));
+                        scale * 1.4426950408889634f, PROF ? g_attn_prof : (long long*)nullptr, hstride));
   TG_COUNT_LAUNCH();
   return 0;
 }
@@ -897,6 +902,7 @@ static int launch_attn_tc2(const __half* Q, const __half* K, const __half* V, in
 template <int CH>
 static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
                           int B, int heads, int N, int d, float scale, cudaStream_t st) {
+  if constexpr (CH == 3) return launch_attn_tc_v<3, 0, false>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
   const int var = attn_variant();
   if (CH == 1 && var == 3 && N % (2 * ATQ) == 0) {  // two query tiles per CTA, alternating exponentials
     if (g_attn_prof != nullptr) return launch_attn_tc2<true>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
@@ -913,11 +919,15 @@ static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int
 // Q/K/V: [B*N, heads * CH * 64] views (head h at column h * CH * 64, columns >= d zero), CH = 1 for d <= 56, 2 for d <= 120
 int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
                  int B, int heads, int N, int d, float scale, cudaStream_t st) {
-  TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d >= 8 && d + 1 <= 2 * ATD, "attention_tc: N=%d (multiple of 128) d=%d (8..120, multiple of 8)", N, d);
+  TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d >= 8 && (d + 1 <= 2 * ATD || (d % 16 == 0 && d <= 176)),
+           "attention_tc: N=%d (multiple of 128) d=%d (8..120 multiple of 8, or 128..176 multiple of 16)", N, d);
   TG_CHECK(ldo % 8 == 0 && (d * 2) % 16 == 0, "attention_tc: output pitch/head offset must be 16B aligned");
   TG_CHECK(ldq % 8 == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0, "attention_tc: Q must be 16-byte aligned with a pitch multiple of 8");
   if (d + 1 <= ATD) return launch_attn_tc<1>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
-  return launch_attn_tc<2>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
+  if (d + 1 <= 2 * ATD) return launch_attn_tc<2>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
+  TG_CHECK((reinterpret_cast<uintptr_t>(K) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (d * 2) % 16 == 0,
+           "attention_tc: packed heads need 16-byte aligned K / V");
+  return launch_attn_tc<3>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);  // packed heads (see the header)
 }
 
 }  // namespace tg

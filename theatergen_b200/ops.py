@@ -218,7 +218,7 @@ def attention(q, k, v, B, heads, scale=None, out=None, causal=False):
 
 def attention_tc(q, k, v, B, heads, d, scale=None, out=None):
     """tcgen05 flash attention: q/k/v are [B*N, heads*P] views, every head padded with zero columns to P = 64 (d <= 56)
-    or P = 128 (d <= 120)."""
+    or P = 128 (d <= 120); for 128 <= d <= 176 (d % 16 == 0) the heads are packed: [B*N, heads*d] views."""
     _chk16(q, k, v, out)
     N = q.shape[0] // B
     if scale is None:

@@ -311,6 +311,9 @@ class _BlockNet:
             a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], Bu, HEADS, C // HEADS)
         elif t["qkv_pad"]:
             raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
+        elif (H * W) % 128 == 0 and (C // HEADS) % 16 == 0 and C // HEADS <= 176 and os.environ.get("TG_ATTN_TC160", "1") != "0":
+            # d = 160 at 16x16: packed heads on the tcgen05 kernel (three 64-column chunks per head)
+            a = ops.attention_tc(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS, C // HEADS)
         else:
             a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS)
         h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)

@@ -32,3 +32,21 @@ for N, d in ((4096, 40), (1024, 80)):
         q, k, v = [torch.randn(B * N, heads * d, device="cuda").half() for _ in range(3)]
         ms = timeit(lambda: ops.attention(q, k, v, B, heads, out=out))
         print(f"mma.sync B={B} N={N} d={d}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s")
+
+# d = 160 at 16x16 (N = 256): packed heads on the tcgen05 kernel vs the mma.sync kernel, device time from a CUDA graph
+N, d = 256, 160
+q, k, v = [torch.randn(B * N, heads * d, device="cuda").half() for _ in range(3)]
+out = torch.empty((B * N, heads * d), dtype=torch.float16, device="cuda")
+for name, f in (("tcgen05 packed", lambda: ops.attention_tc(q, k, v, B, heads, d, out=out)),
+                ("mma.sync", lambda: ops.attention(q, k, v, B, heads, out=out))):
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20): f()
+    g.replay(); torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(5): g.replay()
+    e.record(); torch.cuda.synchronize()
+    print(f"{name} B={B} N={N} d={d}: {s.elapsed_time(e) / 100 * 1e3:.1f} us")
