@@ -89,6 +89,21 @@ int tg_upsample2x_conv3x3(const tg_half* X, int B, int H, int W, int Cin, const 
 int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, int HW, const tg_half* gamma,
                  const tg_half* beta, float eps, int silu, tg_half* out, float* workspace, void* stream);
 
+/* Folded cross-attention (no reference counterpart as an op; replaces, per layer, attn2.to_q + the two softmaxes + the
+ * P.V products + attn2.to_out of IPAttnProcessor.__call__, ip_adapter/attention_processor.py:461-553, for levels whose
+ * images have a multiple of 256 tokens).  The context is constant along a trajectory, so the caller folds it ONCE into
+ *   Kf[b][h*96 + j][c] = scale*log2(e) * sum_dd K[b][j][h*d+dd] * Wq[h*d+dd][c]      (keys: slots 0..n_text-1 text,
+ *   Vf[b][c][h*96 + j] =                 sum_dd V[b][j][h*d+dd] * Wo[c][h*d+dd]        80..80+n_ip-1 image tokens, rest 0)
+ * and a step needs two GEMMs with a per-image B operand:
+ *   tg_cross_scores: P[B*HW, heads*96] = per head { softmax over the text slots | ip_scale[b] * softmax over the image
+ *                    slots | 0 elsewhere } of X[B*HW, C] . Kf[b]^T          (softmax in the GEMM epilogue, fp32)
+ *   tg_cross_apply : out[B*HW, C] = P . Vf[b]^T + bias + residual
+ * P holds the probabilities the reference's get_attention_scores returns (fp16), so attention-map capture is a slice. */
+int tg_cross_scores(const tg_half* X, int ldx, const tg_half* Kf, int B, int HW, int C, int heads, int n_text, int n_ip,
+                    const float* ip_scale, tg_half* P, int ldp, void* stream);
+int tg_cross_apply(const tg_half* P, int ldp, const tg_half* Vf, int B, int HW, int C, int heads, const tg_half* bias,
+                   const tg_half* residual, int ldr, tg_half* out, int ldc, void* stream);
+
 /* tg_gemm / tg_conv3x3 keep a split-K workspace (fp32 partials + arrival counters) per device and SLOT.  Launches that
  * may run concurrently on different streams must use different slots (0..3); the slot is a property of the calling
  * host thread and applies to the launches it enqueues afterwards.  Default slot 0.  (No reference counterpart: the

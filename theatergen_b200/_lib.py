@@ -28,6 +28,8 @@ _SIGS = {
     "tg_conv3x3_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp]),
     "tg_upsample2x_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, vp]),
     "tg_gemm_set_scratch_slot": (ci, [ci]),
+    "tg_cross_scores": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
+    "tg_cross_apply": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
     "tg_gemm_set_stats": (ci, [vp, ci]),
     "tg_groupnorm_apply": (ci, [vp, ci, vp, vp, vp, ci, vp, vp, ci, ci, ci, ci, vp, vp, cf, ci, vp, vp]),
     "tg_groupnorm_tune": (ci, [ci, ci, ci]),

@@ -42,6 +42,24 @@ int tg_gemm(const tg_half* A1, int lda1, int K1, const tg_half* A2, int lda2, co
   return tg::gemm_linear(H(A1), lda1, K1, H(A2), lda2, H(Wt), M, N, K, e, HM(out), ldc, ST(stream));
 }
 
+int tg_cross_scores(const tg_half* X, int ldx, const tg_half* Kf, int B, int HW, int C, int heads, int n_text, int n_ip,
+                    const float* ip_scale, tg_half* P, int ldp, void* stream) {
+  TG_CHECK(X && Kf && P, "tg_cross_scores: null pointer");
+  TG_CHECK(B > 0 && HW > 0 && heads > 0 && heads % 2 == 0 && C % 64 == 0, "tg_cross_scores: B=%d HW=%d heads=%d C=%d", B, HW, heads, C);
+  tg::EpilogueSpec e;
+  e.act = 5; e.b_img_rows = HW; e.sm_text = n_text; e.sm_ip = n_ip; e.sm_ipscale = ip_scale;
+  return tg::gemm_linear(H(X), ldx, C, nullptr, 0, H(Kf), B * HW, heads * 96, C, e, HM(P), ldp, ST(stream));
+}
+
+int tg_cross_apply(const tg_half* P, int ldp, const tg_half* Vf, int B, int HW, int C, int heads, const tg_half* bias,
+                   const tg_half* residual, int ldr, tg_half* out, int ldc, void* stream) {
+  TG_CHECK(P && Vf && out, "tg_cross_apply: null pointer");
+  TG_CHECK(B > 0 && HW > 0 && heads > 0 && C % 64 == 0, "tg_cross_apply: B=%d HW=%d heads=%d C=%d", B, HW, heads, C);
+  tg::EpilogueSpec e;
+  e.bias = H(bias); e.residual = H(residual); e.ldr = ldr; e.b_img_rows = HW;
+  return tg::gemm_linear(H(P), ldp, heads * 96, nullptr, 0, H(Vf), B * HW, C, heads * 96, e, HM(out), ldc, ST(stream));
+}
+
 int tg_conv3x3(const tg_half* X, int B, int Hh, int W, int Cin, const tg_half* Wt, int Cout, const tg_half* bias,
                const tg_half* rowbias, int rowbias_ld, const tg_half* residual, int ldr, int act, float out_scale,
                tg_half* out, int ldc, void* stream) {

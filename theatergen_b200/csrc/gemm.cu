@@ -61,7 +61,15 @@ struct GemmArgs {
   int rows_per_image, rowbias_ld;
   const __half* residual;
   int ldr;
-  int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64), 3 gelu(erf)
+  int act;  // 0 none, 1 silu, 2 geglu (tile columns packed [32 value | 32 gate] per 64), 3 gelu(erf), 5 key softmax
+  // per-image B operand (folded cross-attention, tg_cross_scores / tg_cross_apply): image i = row / img_rows multiplies
+  // rows [i * N, (i + 1) * N) of the stacked B matrix; 0 = one weight matrix for every row
+  int img_rows;
+  // act 5: the tile's columns are heads of 96 key slots (BN = 192: two heads); every output row becomes, per head, the
+  // text softmax over slots [0, sm_text) and the image-token softmax over slots [80, 80 + sm_ip) times sm_ipscale[image];
+  // the other slots are written as zeros.  Scores arrive already multiplied by scale * log2(e).
+  int sm_text, sm_ip;
+  const float* sm_ipscale;
   float out_scale;
   int num_m, num_n, splits;
   int patch_bytes, ky_stride;  // KY3 convolution: bytes of the (box_h + 2)-row input patch, bytes of one image row in it
@@ -268,6 +276,12 @@ __device__ __forceinline__ void chunk_stats(const GemmArgs& g, const uint8_t* bu
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float p;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(x));
+  return p;
+}
+
 // residual prefetch (global, row-contiguous 64 bytes per thread): issued one chunk ahead so its latency overlaps the
 // accumulator wait / the previous chunk's math
 __device__ __forceinline__ void load_residual(const GemmArgs& g, uint4 (&res)[4], int m, int n, bool row_ok) {
@@ -430,8 +444,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             }
           }
           if (leader) {
-            if (PAIR) tma_load_3d_2sm(sb, &tmB, fb, 0, n0 + rank * (BN / 2), kb);  // my half of the weight tile
-            else tma_load_3d(sb, &tmB, &full_bar[s], 0, n0, kb);
+            const int nb = g.img_rows > 0 ? n0 + (m0 / g.img_rows) * g.N : n0;  // per-image B: the image's block of rows
+            if (PAIR) tma_load_3d_2sm(sb, &tmB, fb, 0, nb + rank * (BN / 2), kb);  // my half of the weight tile
+            else tma_load_3d(sb, &tmB, &full_bar[s], 0, nb, kb);
           }
         }
       }
@@ -635,6 +650,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         continue;
       }
 
+      if constexpr (BN == 192) {
+        if (g.act == 5) {
+          // ---- key softmax (folded cross-attention scores): this warp owns head `half` of the tile = 96 key slots of
+          // its 32 rows; the whole score row of the head sits in registers, so the accumulator is released right after
+          // the three tcgen05.ld and both softmaxes are plain per-thread loops ----
+          mbar_wait(&acc_full[as], (j >> 1) & 1);
+          tc_fence_after();
+          float sc[96];
+          {
+            uint32_t r0[32], r1[32], r2[32];
+            tmem_ld_32x32b_x32(lane_addr + half * 96, r0);
+            tmem_ld_32x32b_x32(lane_addr + half * 96 + 32, r1);
+            tmem_ld_32x32b_x32(lane_addr + half * 96 + 64, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              sc[i] = __uint_as_float(r0[i]);
+              sc[32 + i] = __uint_as_float(r1[i]);
+              sc[64 + i] = __uint_as_float(r2[i]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(&acc_empty[as]);
+          float mt = -INFINITY, mi = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 80; ++i) mt = fmaxf(mt, i < g.sm_text ? sc[i] : -INFINITY);
+#pragma unroll
+          for (int i = 80; i < 96; ++i) mi = fmaxf(mi, i - 80 < g.sm_ip ? sc[i] : -INFINITY);
+          float st = 0.f, si = 0.f;
+#pragma unroll
+          for (int i = 0; i < 80; ++i) {
+            sc[i] = i < g.sm_text ? ex2_approx(sc[i] - mt) : 0.f;
+            st += sc[i];
+          }
+#pragma unroll
+          for (int i = 80; i < 96; ++i) {
+            sc[i] = i - 80 < g.sm_ip ? ex2_approx(sc[i] - mi) : 0.f;
+            si += sc[i];
+          }
+          const float it_ = 1.f / st;
+          const float ii_ = (g.sm_ip > 0 && row_ok) ? __ldg(g.sm_ipscale + m / g.img_rows) / si : 0.f;
+#pragma unroll
+          for (int i = 0; i < 80; ++i) sc[i] *= it_;
+#pragma unroll
+          for (int i = 80; i < 96; ++i) sc[i] *= ii_;
+#pragma unroll
+          for (int k = 0; k < 3; ++k, ++chunk_ctr) {
+            uint8_t* buf = my_stage + (chunk_ctr & 1) * (EPI_BUF_BYTES / 2);
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            uint8_t* stage_row = buf + lane * 64;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                h[jj] = __floats2half2_rn(sc[k * 32 + i * 8 + jj * 2], sc[k * 32 + i * 8 + jj * 2 + 1]);
+              *reinterpret_cast<uint4*>(stage_row + ((i ^ ((lane >> 1) & 3)) << 4)) = o;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              store_chunk(&tmC, buf, n0 + half * 96 + k * 32, m0 + q * 32, 0);
+              bulk_commit();
+            }
+          }
+          continue;
+        }
+      }
       const int step = g.act == 2 ? 2 * EC : EC;  // accumulator columns consumed per EC output columns
       const int c_first = half * step;
       uint4 res_next[4];
@@ -774,7 +860,8 @@ static int launch_gemm(const CUtensorMap& a1, const CUtensorMap& a2, const __hal
   if (KY3) {
     if (make_tmap_w_ky3(&b, Wt, g.N, g.Cin, BN / 2)) return -1;
   } else {
-    if (make_tmap_kchunks(&b, Wt, g.N, g.K, PAIR ? BN / 2 : BN, KPS)) return -1;
+    const uint64_t b_rows = g.img_rows > 0 ? (uint64_t)g.N * (g.M / g.img_rows) : (uint64_t)g.N;  // per-image B: stacked blocks
+    if (make_tmap_kchunks(&b, Wt, b_rows, g.K, PAIR ? BN / 2 : BN, KPS)) return -1;
   }
   const int rows_m = PAIR ? (g.num_m + 1) / 2 : g.num_m;
   const int work = rows_m * g.num_n * g.splits;
@@ -826,6 +913,7 @@ static unsigned long long tile_key(int M, int N, int K, int act, int conv) {
 static bool tile_cfg_valid(int M, int N, int K, int act, int bn, int split, int pair) {
   if (bn != 256 && bn != 192 && bn != 160 && bn != 128 && bn != 64) return false;
   if (N % bn || (act == 2 && (bn % 128 || split != 1))) return false;
+  if (act == 5 && (bn != 192 || split != 1)) return false;
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
   if (pair != 0 && pair != 1) return false;
   if (pair && num_m < 2) return false;
@@ -853,6 +941,12 @@ int gemm_force_tile(int bn, int split, int pair) {  // bn = 0 switches the overr
 static void pick_tile(int M, int N, int K, int act, int conv, int patch_bytes, int num_sms, int* bn_out, int* split_out,
                       int* pair_out) {
   const int num_m = (M + BM - 1) / BM, nk = K / BK;
+  if (act == 5) {  // key softmax: a tile is two whole heads (2 x 96 key slots), never split along K
+    *bn_out = 192;
+    *split_out = 1;
+    *pair_out = (pair_enabled() && num_m >= 2 && nk >= 10) ? 1 : 0;
+    return;
+  }
   if (!g_tuned.empty()) {
     auto it = g_tuned.find(tile_key(M, N, K, act, conv));
     if (it != g_tuned.end()) {
@@ -913,6 +1007,14 @@ static int dispatch(const CUtensorMap& a1, const CUtensorMap& a2, GemmArgs g, co
   if (g.stats)
     TG_CHECK(g.act != 2 && g.stats_hw > 0 && g.stats_hw % 32 == 0 && g.M % g.stats_hw == 0,
              "GroupNorm statistics epilogue: rows per image %d must be a multiple of 32 dividing M=%d (no GEGLU)", g.stats_hw, g.M);
+  if (g.img_rows > 0)
+    TG_CHECK(g.mode == 0 && g.M % g.img_rows == 0 && g.img_rows % (2 * BM) == 0,
+             "per-image B operand: rows per image %d must be a multiple of %d dividing M=%d (linear mode)", g.img_rows, 2 * BM, g.M);
+  if (g.act == 5)
+    TG_CHECK(g.N % 192 == 0 && g.img_rows > 0 && g.sm_text > 0 && g.sm_text <= 80 && g.sm_ip >= 0 && g.sm_ip <= 16 &&
+                 (g.sm_ip == 0 || g.sm_ipscale != nullptr) && !g.bias && !g.rowbias && !g.residual && !g.stats,
+             "key-softmax epilogue: N=%d must be heads x 96, text keys %d <= 80, image keys %d <= 16, no other epilogue terms",
+             g.N, g.sm_text, g.sm_ip);
   DeviceScratch* sc;
   if (get_scratch(&sc)) return -1;
   const int n_out = g.act == 2 ? g.N / 2 : g.N;
@@ -979,6 +1081,10 @@ static void fill_args(GemmArgs& g, const EpilogueSpec& e) {
   g.out_scale = e.out_scale;
   g.stats = reinterpret_cast<unsigned long long*>(e.stats);
   g.stats_hw = e.stats_hw;
+  g.img_rows = e.b_img_rows;
+  g.sm_text = e.sm_text;
+  g.sm_ip = e.sm_ip;
+  g.sm_ipscale = e.sm_ipscale;
 }
 
 int gemm_linear(const __half* A1, int lda1, int K1, const __half* A2, int lda2, const __half* Wt, int M, int N,

@@ -18,6 +18,10 @@ struct EpilogueSpec {
   // stats[image = row / stats_hw][column pair][2] += 2^24 x (sum, sum of squares) as 64-bit integers; zeroed by the caller
   long long* stats = nullptr;
   int stats_hw = 0;
+  // per-image B operand + key-softmax epilogue (act 5): the folded cross-attention GEMMs (gemm.cu GemmArgs)
+  int b_img_rows = 0;
+  int sm_text = 0, sm_ip = 0;
+  const float* sm_ipscale = nullptr;
 };
 
 // out[M,N] = epi( [A1 | A2][M,K] * Wt[N,K]^T )

@@ -91,6 +91,7 @@ class StepGraph:
 
     def capture(self):
         from . import _lib
+        self.set_context()  # the per-image operands of the folded cross-attention layers must exist before the capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):

@@ -117,6 +117,47 @@ def gemm(a, w, bias=None, *, a2=None, rowbias=None, rows_per_image=1, residual=N
     return out
 
 
+CROSS_SLOTS = 96  # key slots per head of the folded cross-attention: text keys at 0.., image tokens at 80.., rest zero
+
+
+def cross_scores(x, kf, n_text, n_ip, ip_scale=None, out=None):
+    """Folded cross-attention, first half (include/theatergen.h tg_cross_scores): x [B*HW, C], kf [B, heads*96, C] ->
+    probabilities [B*HW, heads*96] (text softmax | ip_scale[b] * image-token softmax | zeros), softmax in the GEMM epilogue."""
+    _chk16(x, kf, out)
+    B, N, C = kf.shape
+    M = x.shape[0]
+    assert kf.is_contiguous() and x.shape[1] == C and N % (2 * CROSS_SLOTS) == 0 and M % B == 0
+    heads, HW = N // CROSS_SLOTS, M // B
+    if n_ip:
+        assert ip_scale is not None and ip_scale.dtype == torch.float32 and ip_scale.numel() == B and ip_scale.is_cuda
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    rc = _timed("gemm_tc_kernel", 2.0 * M * N * C, 2.0 * (M * C + B * N * C + M * N),
+                lambda: _lib.lib().tg_cross_scores(_p(x), x.stride(0), _p(kf), B, HW, C, heads, n_text, n_ip,
+                                                   _p(ip_scale) if n_ip else 0, _p(out), out.stride(0), _stream()),
+                tag=f"xscores M={M} N={N} K={C}")
+    _lib.check(rc, "tg_cross_scores")
+    return out
+
+
+def cross_apply(p, vf, bias=None, residual=None, out=None):
+    """Folded cross-attention, second half (tg_cross_apply): p [B*HW, heads*96], vf [B, C, heads*96] ->
+    [B*HW, C] = p @ vf[b].T + bias + residual."""
+    _chk16(p, vf, bias, residual, out)
+    B, C, N = vf.shape
+    M = p.shape[0]
+    assert vf.is_contiguous() and p.shape[1] == N and N % CROSS_SLOTS == 0 and M % B == 0
+    if out is None:
+        out = torch.empty((M, C), dtype=torch.float16, device=p.device)
+    rc = _timed("gemm_tc_kernel", 2.0 * M * N * C, 2.0 * (M * N + B * N * C + M * C + (M * C if residual is not None else 0)),
+                lambda: _lib.lib().tg_cross_apply(_p(p), p.stride(0), _p(vf), B, M // B, C, N // CROSS_SLOTS, _p(bias),
+                                                  _p(residual), 0 if residual is None else residual.stride(0), _p(out),
+                                                  out.stride(0), _stream()),
+                tag=f"xapply M={M} N={C} K={N}")
+    _lib.check(rc, "tg_cross_apply")
+    return out
+
+
 def conv3x3(x, w, bias=None, *, rowbias=None, residual=None, act=TG_ACT_NONE, out_scale=1.0, out=None, stats=None):
     """x [B,H,W,Cin] NHWC, w [Cout,3,3,Cin] -> [B,H,W,Cout] (pad 1, stride 1)."""
     _chk16(x, w, bias, rowbias, residual, out)

@@ -21,6 +21,9 @@ from .weights import pack_conv3x3, pack_geglu, pack_upsample_conv3x3
 
 BLOCK_OUT = (320, 640, 1280, 1280)
 HEADS = 8
+# channel widths whose cross-attention layers run folded (TG_CROSS_FOLD="640,1280" restricts it, "" = none); the mid block (8x8: an image
+# has fewer rows than a GEMM tile) always keeps the attention kernel
+CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "320,640,1280").split(",") if v)
 
 
 class UNetOutput:
@@ -136,9 +139,31 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
             k_ = f"{tb_}.attn2.processor.{n_}.weight"
             rows.append(g(k_) if has_key(k_) else torch.zeros_like(rows[0]))
     t["kv_rows"] = len(rows)
+    if c in CROSS_FOLD_C and not p.startswith("mid_block"):
+        fold_cross_weights(t, rows)
     t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
     t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
     return t, rows
+
+
+def _fold_pair(t, wk, wv):
+    """[heads*C | heads*C, 768]: the key rows  scale*log2(e) * Wq_h^T Wk_h  and the value rows  Wo_h Wv_h  of every head."""
+    c, d_ = t["C"], t["C"] // HEADS
+    wq = t["q2w"].float().view(HEADS, d_, c)
+    wo = t["o2w"].float().view(c, HEADS, d_)
+    fk = torch.einsum("hdc,hdk->hck", wq, wk.float().view(HEADS, d_, -1)) * (d_ ** -0.5 * 1.4426950408889634)
+    fv = torch.einsum("chd,hdk->hck", wo, wv.float().view(HEADS, d_, -1))
+    return torch.cat([fk.reshape(HEADS * c, -1), fv.reshape(HEADS * c, -1)], 0).half().contiguous()
+
+
+def fold_cross_weights(t, rows):
+    """Folded cross-attention (include/theatergen.h tg_cross_scores): attn2.to_q is folded into the key projection and
+    attn2.to_out into the value projection of every head, so the per-trajectory context projection yields, per image, a
+    [heads*96, C] score operand and a [C, heads*96] output operand and a denoise step runs two GEMMs instead of
+    to_q + attention + to_out.  Same algebra as attention_processor.py:461-553, summed in a different order."""
+    t["fkt"] = _fold_pair(t, rows[0], rows[1])
+    if len(rows) == 4:
+        t["fki"] = _fold_pair(t, rows[2], rows[3])
 
 
 def downsample_conv(x, w9, bias, cout, pad_lo=1, act=ops.TG_ACT_NONE, stats=None):
@@ -219,7 +244,39 @@ class _BlockNet:
         [B*T, sum of 2C (text) + 2C (image tokens) per layer].  They depend on the prompt / image tokens only -- not on the
         timestep or the latents -- so a denoise loop computes them ONCE per trajectory (engine.StepGraph.set_context)
         instead of once per step like the reference's processors do (attention_processor.py:475-476, 497-498): same values."""
-        return ops.gemm(ctx.reshape(ctx.shape[0] * ctx.shape[1], -1), self.w["ctxkv.w"], out=out)
+        kv = ops.gemm(ctx.reshape(ctx.shape[0] * ctx.shape[1], -1), self.w["ctxkv.w"], out=out)
+        self._fold_context(ctx, kv)
+        return kv
+
+    def _fold_context(self, ctx, kv):
+        """Per-image operands of the folded cross-attention layers (fold_cross_weights), kept as `kv.fold[layer] = (kf
+        [B, heads, 96, C], vf [B, C, heads, 96])`: allocated on first use, refreshed in place afterwards so a captured
+        graph keeps reading the same buffers."""
+        fold = getattr(kv, "fold", None)
+        if fold is None:
+            fold = kv.fold = {}
+        B, T = ctx.shape[:2]
+        n_ip = self.num_ip_tokens if getattr(self, "has_ip", False) else 0
+        n_text = T - n_ip
+        ct = ci = None
+        for p, t in self.transformers.items():
+            if "fkt" not in t:
+                continue
+            C = t["C"]
+            if ct is None:
+                ct = ctx[:, :n_text].reshape(B * n_text, -1)
+                ci = ctx[:, n_text:].reshape(B * n_ip, -1) if n_ip else None
+            if p not in fold or fold[p][0].shape[0] != B:
+                fold[p] = (torch.zeros((B, HEADS, ops.CROSS_SLOTS, C), dtype=torch.float16, device=ctx.device),
+                           torch.zeros((B, C, HEADS, ops.CROSS_SLOTS), dtype=torch.float16, device=ctx.device))
+            kf, vf = fold[p]
+            pr = ops.gemm(ct, t["fkt"]).view(B, n_text, 2, HEADS, C)
+            kf[:, :, :n_text].copy_(pr[:, :, 0].permute(0, 2, 1, 3))
+            vf[..., :n_text].copy_(pr[:, :, 1].permute(0, 3, 2, 1))
+            if n_ip:
+                pi = ops.gemm(ci, t["fki"]).view(B, n_ip, 2, HEADS, C)
+                kf[:, :, 80:80 + n_ip].copy_(pi[:, :, 0].permute(0, 2, 1, 3))
+                vf[..., 80:80 + n_ip].copy_(pi[:, :, 1].permute(0, 3, 2, 1))
 
     def _time_and_context(self, t_dev, ctx, B, ctxkv=None):
         w = self.w
@@ -322,21 +379,32 @@ class _BlockNet:
             x = x.view(Bu, H * W * C).index_select(0, share)
         # cross attention (+ image tokens)
         ln = ops.layernorm(h, t["norm2g"], t["norm2b"])
-        q = ops.gemm(ln, t["q2w"])
-        o = t["kv_off"]
         probs, b0 = None, 0
-        if capture is not None and (save_keys is None or t["key"] in save_keys):
+        want_probs = capture is not None and (save_keys is None or t["key"] in save_keys)
+        if want_probs:
             b0 = capture_b0 if capture_b0 is not None else (B // 2 if cond_only else 0)
-            probs = torch.empty((B - b0, HEADS, H * W, n_text), dtype=torch.float16, device=x.device)
-        a = ops.attention_cross_ip(q, ctxkv[:, o:o + C], ctxkv[:, o + C:o + 2 * C],
-                                   ctxkv[:, o + 2 * C:o + 3 * C] if n_ip else None,
-                                   ctxkv[:, o + 3 * C:o + 4 * C] if n_ip else None, B, HEADS, n_text, n_ip,
-                                   ip_scale=ip_scale if n_ip else None, probs=probs, probs_b0=b0)
+        fold = getattr(ctxkv, "fold", {}).get(p) if (H * W) % 256 == 0 else None
+        if fold is not None:
+            # folded layer: probabilities = softmax epilogue of ln . Kf[b]^T, output = P . Vf[b]^T + bias + residual
+            NS = HEADS * ops.CROSS_SLOTS
+            pm = ops.cross_scores(ln, fold[0].view(B, NS, C), n_text, n_ip, ip_scale if n_ip else None)
+            if want_probs:
+                probs = pm.view(B, H * W, HEADS, ops.CROSS_SLOTS)[b0:, :, :, :n_text].permute(0, 2, 1, 3).contiguous()
+            h = ops.cross_apply(pm, fold[1].view(B, C, NS), t["o2b"], residual=h)
+        else:
+            q = ops.gemm(ln, t["q2w"])
+            o = t["kv_off"]
+            if want_probs:
+                probs = torch.empty((B - b0, HEADS, H * W, n_text), dtype=torch.float16, device=x.device)
+            a = ops.attention_cross_ip(q, ctxkv[:, o:o + C], ctxkv[:, o + C:o + 2 * C],
+                                       ctxkv[:, o + 2 * C:o + 3 * C] if n_ip else None,
+                                       ctxkv[:, o + 3 * C:o + 4 * C] if n_ip else None, B, HEADS, n_text, n_ip,
+                                       ip_scale=ip_scale if n_ip else None, probs=probs, probs_b0=b0)
+            h = ops.gemm(a, t["o2w"], t["o2b"], residual=h)
         if probs is not None:
             if token_idx is not None:
                 probs = probs[..., token_idx:token_idx + 1] if isinstance(token_idx, int) else probs[..., token_idx]
             capture[t["key"]] = probs
-        h = ops.gemm(a, t["o2w"], t["o2b"], residual=h)
         # feed forward (GEGLU fused in the GEMM epilogue)
         ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
         ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
@@ -411,6 +479,9 @@ class TGUNet(_BlockNet):
             for j, name in enumerate(("to_k_ip", "to_v_ip")):
                 wt = ip_state_dict[f"{idx}.{name}.weight"].to(device=self.device, dtype=torch.float16)
                 self.w["ctxkv.w"][o + (2 + j) * c:o + (3 + j) * c].copy_(wt)
+            t = self.transformers[p]
+            if "fki" in t:  # folded layer: the image-token operands follow the new weights
+                t["fki"] = _fold_pair(t, self.w["ctxkv.w"][o + 2 * c:o + 3 * c], self.w["ctxkv.w"][o + 3 * c:o + 4 * c])
 
     def weight_bytes(self):
         n = sum(v.numel() for v in self.w.values())
