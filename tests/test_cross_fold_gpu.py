@@ -144,3 +144,31 @@ def test_unet_forward_folded_vs_attention_kernels():
         a, b = caps["folded"][k].float(), caps["kernels"][k].float()
         assert a.shape == b.shape
         assert (a - b).abs().max().item() < 2e-3, k
+
+
+def test_unet_forward_ff2_proj_out_as_one_gemm():
+    """ff.net.2 (+h) and proj_out (+x) as ONE GEMM over [h | ff] with the weights [Wpo | Wpo W2] (unet.pack_transformer) against
+    the two GEMMs of the reference's op order (ip_adapter/attention.py:339-367, transformer_2d.py:330-342), both vs the oracle."""
+    from oracle import unet as OU
+    from theatergen_b200 import unet as U
+    sd = OU.synth_state_dict(1234)
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(2, 4, 64, 64, generator=g).half().cuda()
+    ctx = torch.randn(2, 81, 768, generator=g).half().cuda()
+    outs = {}
+    saved = U.FOLD_FF2_PROJ_OUT
+    try:
+        for name, fold in (("one", True), ("two", False)):
+            U.FOLD_FF2_PROJ_OUT = fold
+            net = U.TGUNet(sd, "cuda:0")
+            assert any("fpw" in t for t in net.transformers.values()) == fold
+            outs[name] = net(lat, 301, encoder_hidden_states=ctx).sample.float()
+    finally:
+        U.FOLD_FF2_PROJ_OUT = saved
+    sd32 = {k: v.half().float().cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = OU.unet_forward(sd32, lat.float(), 301, ctx.float(), ip_scale=1.0)
+    e1 = (outs["one"] - ref).abs().max().item()
+    e2 = (outs["two"] - ref).abs().max().item()
+    print(f"max|eps - fp32 oracle|: one GEMM {e1:.3e}, two GEMMs {e2:.3e}")
+    assert e1 <= max(1.5 * e2, 4e-3), (e1, e2)

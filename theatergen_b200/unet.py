@@ -23,6 +23,7 @@ BLOCK_OUT = (320, 640, 1280, 1280)
 HEADS = 8
 # channel widths whose cross-attention layers run folded (TG_CROSS_FOLD="640,1280" restricts it, "" = none); the mid block (8x8: an image
 # has fewer rows than a GEMM tile) always keeps the attention kernel
+FOLD_FF2_PROJ_OUT = os.environ.get("TG_FOLD_FF2", "1") != "0"
 CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "320,640,1280").split(",") if v)
 
 
@@ -143,6 +144,12 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
         fold_cross_weights(t, rows)
     t["ff1w"], t["ff1b"] = pack_geglu(g(f"{tb_}.ff.net.0.proj.weight"), g(f"{tb_}.ff.net.0.proj.bias"))
     t["ff2w"], t["ff2b"] = g(f"{tb_}.ff.net.2.weight"), g(f"{tb_}.ff.net.2.bias")
+    if FOLD_FF2_PROJ_OUT:
+        # ff.net.2 (+ residual h) followed by proj_out (+ residual x) is linear in (h, ff): one GEMM over the concatenation
+        #   out = [h | ff] . [Wpo | Wpo W2]^T + (Wpo b2 + bpo) + x        (same flops, one launch and one [M, C] round trip less)
+        wpo, w2 = t["pow"].float(), t["ff2w"].float()
+        t["fpw"] = torch.cat([wpo, wpo @ w2], 1).half().contiguous()
+        t["fpb"] = (wpo @ t["ff2b"].float() + t["pob"].float()).half()
     return t, rows
 
 
@@ -408,8 +415,10 @@ class _BlockNet:
         # feed forward (GEGLU fused in the GEMM epilogue)
         ln = ops.layernorm(h, t["norm3g"], t["norm3b"])
         ff = ops.gemm(ln, t["ff1w"], t["ff1b"], act=ops.TG_ACT_GEGLU)
-        h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
         so = self._take(B, C, H * W)
+        if "fpw" in t:  # ff.net.2 and proj_out as one GEMM over [h | ff] (pack_transformer)
+            return _set(ops.gemm(h, t["fpw"], t["fpb"], a2=ff, residual=x.view(M, C), stats=so).view(B, H, W, C), so)
+        h = ops.gemm(ff, t["ff2w"], t["ff2b"], residual=h)
         return _set(ops.gemm(h, t["pow"], t["pob"], residual=x.view(M, C), stats=so).view(B, H, W, C), so)
 
 
