@@ -344,13 +344,28 @@ class _BlockNet:
         r = self.resnets[p]
         cin, co = r["cin"], r["cout"]
         HW = H * W
+        sc, side = None, None
+        if "scw" in r and getattr(self, "fork_shortcut", False):
+            # the 1x1 shortcut depends on the block input only: a parallel branch (its own stream / graph branch and
+            # split-K slot) beside GroupNorm -> conv1 -> GroupNorm, joined in front of conv2, whose epilogue adds it
+            main, side = torch.cuda.current_stream(), self._shortcut_stream()
+            side.wait_stream(main)
+            _lib.check(_lib.lib().tg_gemm_set_scratch_slot(2), "tg_gemm_set_scratch_slot")
+            try:
+                with torch.cuda.stream(side):
+                    sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
+            finally:
+                _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
         n1 = ops.groupnorm(x1.view(B, HW, -1), r["n1g"], r["n1b"], 1e-5, x2=None if x2 is None else x2.view(B, HW, -1),
                            silu=True, st1=_st(x1), st2=_st(x2))
         sh, so = self._take(B, co, HW), self._take(B, co, HW)
         h = ops.conv3x3(n1.view(B, H, W, cin), r["c1w"], r["c1b"],
                         rowbias=temb_all[:, r["temb_off"]:r["temb_off"] + co], stats=sh)
         n2 = ops.groupnorm(h.view(B, HW, co), r["n2g"], r["n2b"], 1e-5, silu=True, st1=_st(_set(h, sh)))
-        if "scw" in r:
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            sc = sc.view(B, H, W, co)
+        elif "scw" in r:
             sc = ops.gemm(x1.view(B * HW, -1), r["scw"], r["scb"], a2=None if x2 is None else x2.view(B * HW, -1))
             sc = sc.view(B, H, W, co)
         else:
@@ -435,6 +450,7 @@ class TGUNet(_BlockNet):
             self.attn_processors[f"{p}.transformer_blocks.0.attn2.processor"] = IPAttnProcessorHandle(
                 c, cross_attention_dim, 1.0, num_ip_tokens)
         self.ip_scale_per_sample = None  # optional float32 [B] device tensor (co-batched characters)
+        self.fork_shortcut = os.environ.get("TG_SC_FORK", "1") != "0"  # _resnet: shortcut GEMM as a parallel branch
         self._scale_buf = {}
 
     # -------------------------------------------------------------------------------------------------
@@ -499,6 +515,11 @@ class TGUNet(_BlockNet):
         return 2 * n
 
     # -------------------------------------------------------------------------------------------------
+    def _shortcut_stream(self):
+        if getattr(self, "_sc_side", None) is None:
+            self._sc_side = torch.cuda.Stream(device=self.device)
+        return self._sc_side
+
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=self.device)
