@@ -164,6 +164,12 @@ int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, 
  * heads PACKED (head h at column h*d, no padding) -- three 64-column chunks per head. */
 int tg_attention_tc(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
                     int ldo, int B, int heads, int N, int d, float scale, void* stream);
+/* The same kernels on PACKED heads for every head dim (Q/K/V are [B*N, heads*d] views, head h at column h*d, d % 8 == 0,
+ * K / V 16-byte aligned): the fused QKV projection then has 3*heads*d output columns instead of 3*heads*64 (d = 40) or
+ * 3*heads*128 (d = 80).  The 64-column TMA boxes of a head's last chunk reach into the next head (past the tensor: zero
+ * fill); those columns meet zeros of the Q operand in Q K^T and lie beyond the output columns read after P V. */
+int tg_attention_tc_packed(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
+                           int ldo, int B, int heads, int N, int d, float scale, void* stream);
 
 /* IP-Adapter decoupled cross attention (IPAttnProcessor.__call__, ip_adapter/attention_processor.py:478-516):
  *   O = softmax(scale Q Kt^T + add_mask) Vt + ip_scale[b] * softmax(scale Q Ki^T) Vi

@@ -52,18 +52,21 @@ def test_self_attention_tcgen05(B, N, d):
     assert torch.equal(out, ops.attention_tc(flat[:, :P], flat[:, P:2 * P], flat[:, 2 * P:], B, heads, d))
 
 
-@pytest.mark.parametrize("B,N,d,heads", [(10, 256, 160, 8), (2, 128, 160, 8), (1, 1024, 160, 8), (2, 256, 128, 4), (3, 384, 176, 5)])
+@pytest.mark.parametrize("B,N,d,heads", [(10, 256, 160, 8), (2, 128, 160, 8), (1, 1024, 160, 8), (2, 256, 128, 4), (3, 384, 176, 5),
+                                         (2, 4096, 40, 8), (10, 1024, 80, 8), (2, 256, 48, 8), (1, 128, 8, 8), (2, 384, 120, 3),
+                                         (2, 512, 56, 5), (1, 256, 72, 8)])
 def test_self_attention_tcgen05_packed_heads(B, N, d, heads):
-    """d = 160 (the 16x16 level of SD-1.5): heads packed at stride d inside the fused QKV buffer -- three 64-column chunks
-    per head whose last box reaches into the next head / past the tensor -- vs fp32 SDPA and vs the mma.sync kernel.  The
-    NaN rows planted in the NEXT buffer region check that nothing outside a head's columns reaches its output."""
+    """Heads packed at stride d inside the fused QKV buffer (d = 160: the 16x16 level of SD-1.5, three 64-column chunks per
+    head; d = 40 / 80: the 64x64 / 32x32 levels) -- the last box of a head reaches into the next head / past the tensor --
+    vs fp32 SDPA and vs the mma.sync kernel.  The NaN columns planted behind V check that nothing outside the tensor map
+    reaches an output."""
     from theatergen_b200 import ops
     C = heads * d
     qkv = torch.zeros((B * N, 3 * C + 64), dtype=torch.float16, device="cuda")
     qkv[:, :3 * C] = _rand((B * N, 3 * C), 3, 1.2)
     qkv[:, 3 * C:] = float("nan")  # what a box past the last head of V would read if the tensor map were too wide
     q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:3 * C]
-    out = ops.attention_tc(q, k, v, B, heads, d)
+    out = ops.attention_tc(q, k, v, B, heads, d, packed=True)
     assert out.shape == (B * N, C) and bool(torch.isfinite(out).all())
     q4, k4, v4 = [t.float().reshape(B, N, heads, d).transpose(1, 2) for t in (q, k, v)]
     ref = F.scaled_dot_product_attention(q4, k4, v4).transpose(1, 2).reshape(B * N, C)
@@ -71,7 +74,7 @@ def test_self_attention_tcgen05_packed_heads(B, N, d, heads):
     if d == 160:  # the mma.sync kernel is instantiated for SD-1.5's head dims only
         old = ops.attention(q, k, v, B, heads)
         assert (out.float() - old.float()).abs().max().item() < 3e-3
-    assert torch.equal(out, ops.attention_tc(q, k, v, B, heads, d))
+    assert torch.equal(out, ops.attention_tc(q, k, v, B, heads, d, packed=True))
 
 
 def test_self_attention_tcgen05_lazy_rescale():

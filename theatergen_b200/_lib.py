@@ -36,6 +36,7 @@ _SIGS = {
     "tg_layernorm": (ci, [vp, ci, vp, vp, cf, vp, ci, ci, ci, vp]),
     "tg_attention": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, ci, cf, ci, vp]),
     "tg_attention_tc": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
+    "tg_attention_tc_packed": (ci, [vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_attention_cross_ip": (ci, [vp, ci, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, ci, vp, ci, ci, ci, ci, ci, cf, vp]),
     "tg_upsample2x": (ci, [vp, ci, ci, ci, ci, vp, vp]),
     "tg_im2col_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp]),

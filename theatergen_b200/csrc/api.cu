@@ -148,7 +148,13 @@ int tg_attention(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, 
 int tg_attention_tc(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
                     int ldo, int B, int heads, int N, int d, float scale, void* stream) {
   TG_CHECK(Q && K && V && O && N > 0, "tg_attention_tc: bad arguments");
-  return tg::attention_tc(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, N, d, scale, ST(stream));
+  return tg::attention_tc(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, N, d, scale, 0, ST(stream));
+}
+
+int tg_attention_tc_packed(const tg_half* Q, const tg_half* K, const tg_half* V, int ldq, int ldk, int ldv, tg_half* O,
+                           int ldo, int B, int heads, int N, int d, float scale, void* stream) {
+  TG_CHECK(Q && K && V && O && N > 0, "tg_attention_tc_packed: bad arguments");
+  return tg::attention_tc(H(Q), H(K), H(V), ldq, ldk, ldv, HM(O), ldo, B, heads, N, d, scale, 1, ST(stream));
 }
 
 int tg_attention_cross_ip(const tg_half* Q, int ldq, const tg_half* Kt, const tg_half* Vt, const tg_half* Ki,

@@ -274,7 +274,9 @@ attn_tc_kernel(const __half* __restrict__ Q, int ldq, const __grid_constant__ CU
       for (int k = 0; k < ksteps; ++k) {
         uint4 v[2];
         v[0] = __ldg(qrow + 2 * k);
-        v[1] = __ldg(qrow + 2 * k + 1);
+        // packed heads: the columns from d up to the next multiple of 16 belong to the next head (or lie past the row) --
+        // never read, zero in the operand, so whatever the K tile holds there contributes nothing
+        v[1] = (2 * k + 1) * 8 < d ? __ldg(qrow + 2 * k + 1) : make_uint4(0u, 0u, 0u, 0u);
         tmem_st_32x32b_x8(tQ + k * 8 + lane_off, reinterpret_cast<const uint32_t*>(v));
       }
       tmem_st_wait();
@@ -861,16 +863,21 @@ static int attn_variant() {
   return g_attn_variant;
 }
 
+// heads of Q / K / V packed at stride d (no zero columns between them) also for d <= 120: set by attention_tc for the launch
+// it is about to enqueue
+static thread_local bool g_attn_packed = false;
+
 template <int CH, int VAR, bool PROF>
 static int launch_attn_tc_v(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O,
                             int ldo, int B, int heads, int N, int d, float scale, cudaStream_t st) {
+  const bool packed = g_attn_packed;
   using Cfg = AttnCfg<CH>;
   auto kern = attn_tc_kernel<CH, VAR, PROF>;
   TG_SMEM_ATTR_ONCE(kern, Cfg::SMEM);
   CUtensorMap tk, tv;
   // CH = 3 (d = 160): heads packed at stride d -- the 64-column boxes of a head's last chunk reach into the next head (or
   // past the tensor: zero fill); those columns lie beyond the K extent of Q K^T and beyond the output columns that are read
-  const int hstride = CH == 3 ? d : CH * ATD;
+  const int hstride = (CH == 3 || packed) ? d : CH * ATD;
   const uint64_t rows = (uint64_t)B * N, cols = (uint64_t)heads * hstride;
   if (make_tmap_2d(&tk, K, rows, cols, ldk, AT_TPS * ATK)) return -1;
   if (make_tmap_2d(&tv, V, rows, cols, ldv, AT_TPS * ATK)) return -1;
@@ -904,7 +911,7 @@ static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int
                           int B, int heads, int N, int d, float scale, cudaStream_t st) {
   if constexpr (CH == 3) return launch_attn_tc_v<3, 0, false>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
   const int var = attn_variant();
-  if (CH == 1 && var == 3 && N % (2 * ATQ) == 0) {  // two query tiles per CTA, alternating exponentials
+  if (CH == 1 && var == 3 && N % (2 * ATQ) == 0 && !g_attn_packed) {  // two query tiles per CTA, alternating exponentials
     if (g_attn_prof != nullptr) return launch_attn_tc2<true>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
     return launch_attn_tc2<false>(Q, K, V, ldq, ldk, ldv, O, ldo, B, heads, N, d, scale, st);
   }
@@ -917,8 +924,18 @@ static int launch_attn_tc(const __half* Q, const __half* K, const __half* V, int
 }
 
 // Q/K/V: [B*N, heads * CH * 64] views (head h at column h * CH * 64, columns >= d zero), CH = 1 for d <= 56, 2 for d <= 120
+// packed != 0: heads at stride d for every d (Q / K / V are [B*N, heads * d] views): the 64-column boxes of a head's last chunk
+// reach into the next head (or past the tensor: zero fill); those columns meet zeros of the Q operand in Q K^T and lie
+// beyond the output columns that are read in P V.
 int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
-                 int B, int heads, int N, int d, float scale, cudaStream_t st) {
+                 int B, int heads, int N, int d, float scale, int packed, cudaStream_t st) {
+  struct PackedScope {
+    explicit PackedScope(bool p) { g_attn_packed = p; }
+    ~PackedScope() { g_attn_packed = false; }
+  } scope(packed != 0);
+  if (packed)
+    TG_CHECK((reinterpret_cast<uintptr_t>(K) & 15) == 0 && (reinterpret_cast<uintptr_t>(V) & 15) == 0 && (d * 2) % 16 == 0,
+             "attention_tc: packed heads need 16-byte aligned K / V and d %% 8 == 0");
   TG_CHECK(N % ATQ == 0 && d % 8 == 0 && d >= 8 && (d + 1 <= 2 * ATD || (d % 16 == 0 && d <= 176)),
            "attention_tc: N=%d (multiple of 128) d=%d (8..120 multiple of 8, or 128..176 multiple of 16)", N, d);
   TG_CHECK(ldo % 8 == 0 && (d * 2) % 16 == 0, "attention_tc: output pitch/head offset must be 16B aligned");

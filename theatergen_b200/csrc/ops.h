@@ -67,7 +67,7 @@ int attention_flash(const __half* Q, const __half* K, const __half* V, int ldq, 
                     int B, int heads, int Nq, int Nk, int d, float scale, int causal, cudaStream_t st);
 // tcgen05 flash self-attention; Q/K/V head-padded to 64 columns (head h at column h*64), N % 128 == 0, d <= 64
 int attention_tc(const __half* Q, const __half* K, const __half* V, int ldq, int ldk, int ldv, __half* O, int ldo,
-                 int B, int heads, int N, int d, float scale, cudaStream_t st);
+                 int B, int heads, int N, int d, float scale, int packed, cudaStream_t st);
 // text + image-token cross attention (see attn.cu)
 int attention_cross_ip(const __half* Q, int ldq, const __half* Kt, const __half* Vt, const __half* Ki,
                        const __half* Vi, int ldkv, int n_text, int n_ip, const float* ip_scale,

@@ -257,9 +257,10 @@ def attention(q, k, v, B, heads, scale=None, out=None, causal=False):
     return out
 
 
-def attention_tc(q, k, v, B, heads, d, scale=None, out=None):
+def attention_tc(q, k, v, B, heads, d, scale=None, out=None, packed=False):
     """tcgen05 flash attention: q/k/v are [B*N, heads*P] views, every head padded with zero columns to P = 64 (d <= 56)
-    or P = 128 (d <= 120); for 128 <= d <= 176 (d % 16 == 0) the heads are packed: [B*N, heads*d] views."""
+    or P = 128 (d <= 120); for 128 <= d <= 176 (d % 16 == 0) -- and for every d with packed=True -- the heads are packed:
+    [B*N, heads*d] views."""
     _chk16(q, k, v, out)
     N = q.shape[0] // B
     if scale is None:
@@ -267,8 +268,9 @@ def attention_tc(q, k, v, B, heads, d, scale=None, out=None):
     if out is None:
         out = torch.empty((B * N, heads * d), dtype=torch.float16, device=q.device)
     rc = _timed("attn_tc_kernel", 4.0 * B * heads * N * N * d, 2.0 * B * heads * d * 4 * N,
-                lambda: _lib.lib().tg_attention_tc(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out),
-                                                   out.stride(0), B, heads, N, d, float(scale), _stream()))
+                lambda: (_lib.lib().tg_attention_tc_packed if packed else _lib.lib().tg_attention_tc)(
+                    _p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), _p(out), out.stride(0), B, heads, N, d,
+                    float(scale), _stream()))
     _lib.check(rc, "tg_attention_tc")
     return out
 

@@ -23,6 +23,8 @@ BLOCK_OUT = (320, 640, 1280, 1280)
 HEADS = 8
 # channel widths whose cross-attention layers run folded (TG_CROSS_FOLD="640,1280" restricts it, "" = none); the mid block (8x8: an image
 # has fewer rows than a GEMM tile) always keeps the attention kernel
+# self-attention Q/K/V with heads packed at stride d for d = 40 / 80 too (TG_QKV_PACKED=0: zero-padded to 64 / 128 columns)
+QKV_PACKED = os.environ.get("TG_QKV_PACKED", "1") != "0"
 FOLD_FF2_PROJ_OUT = os.environ.get("TG_FOLD_FF2", "1") != "0"
 CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "320,640,1280").split(",") if v)
 
@@ -119,7 +121,7 @@ def pack_transformer(g, dev, p, c, key, kv_off, has_ip, has_key=lambda k: True):
     # tcgen05 attention path: every head padded (zero weight rows) to 64 columns for d = 40 and to 128 (two 64-column
     # chunks) for d = 80; d = 160 stays unpadded on the mma.sync kernel
     d_ = c // HEADS
-    t["qkv_pad"] = 64 if d_ + 1 <= 64 else (128 if d_ + 1 <= 128 else 0)
+    t["qkv_pad"] = 0 if QKV_PACKED else (64 if d_ + 1 <= 64 else (128 if d_ + 1 <= 128 else 0))
     if t["qkv_pad"]:
         pad = t["qkv_pad"]
         padded = torch.zeros((3, HEADS, pad, c), dtype=torch.float16, device=dev)
@@ -390,9 +392,10 @@ class _BlockNet:
             a = ops.attention_tc(qkv[:, :P], qkv[:, P:2 * P], qkv[:, 2 * P:], Bu, HEADS, C // HEADS)
         elif t["qkv_pad"]:
             raise RuntimeError("padded-QKV layers need a token count that is a multiple of 128")
-        elif (H * W) % 128 == 0 and (C // HEADS) % 16 == 0 and C // HEADS <= 176 and os.environ.get("TG_ATTN_TC160", "1") != "0":
-            # d = 160 at 16x16: packed heads on the tcgen05 kernel (three 64-column chunks per head)
-            a = ops.attention_tc(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS, C // HEADS)
+        elif (H * W) % 128 == 0 and (C // HEADS) % 8 == 0 and C // HEADS <= 176 and os.environ.get("TG_ATTN_TC160", "1") != "0":
+            # packed heads on the tcgen05 kernel (d = 160 at 16x16: three 64-column chunks per head; d = 40 / 80 with
+            # QKV_PACKED: the QKV projection has 3C output columns instead of 3 * 8 * 64 / 3 * 8 * 128)
+            a = ops.attention_tc(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS, C // HEADS, packed=True)
         else:
             a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], Bu, HEADS)
         h = ops.gemm(a, t["o1w"], t["o1b"], residual=h)
