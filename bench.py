@@ -65,7 +65,7 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,enforced.power.limit")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -91,8 +91,16 @@ class ClockSampler:
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        def _f(r, i):
+            try:
+                return float(r[i])
+            except (IndexError, ValueError):
+                return None
+        pw = sorted(v for v in (_f(r, 6) for r in self.rows) if v is not None)
+        lim = [v for v in (_f(r, 7) for r in self.rows) if v is not None]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": pw[len(pw) // 2] if pw else None,
+                "power_limit_w": max(lim) if lim else None}
 
 
 # =============================================================================================================
