@@ -21,12 +21,14 @@ from .weights import pack_conv3x3, pack_geglu, pack_upsample_conv3x3
 
 BLOCK_OUT = (320, 640, 1280, 1280)
 HEADS = 8
-# channel widths whose cross-attention layers run folded (TG_CROSS_FOLD="640,1280" restricts it, "" = none); the mid block (8x8: an image
-# has fewer rows than a GEMM tile) always keeps the attention kernel
 # self-attention Q/K/V with heads packed at stride d for d = 40 / 80 too (TG_QKV_PACKED=0: zero-padded to 64 / 128 columns)
 QKV_PACKED = os.environ.get("TG_QKV_PACKED", "1") != "0"
 FOLD_FF2_PROJ_OUT = os.environ.get("TG_FOLD_FF2", "1") != "0"
-CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "320,640,1280").split(",") if v)
+# channel widths whose cross-attention layers run folded (TG_CROSS_FOLD="320,640,1280": every level, "" = none); the mid block
+# (8x8: an image has fewer rows than a GEMM tile) always keeps the attention kernel.  At C = 320 (64x64) the folded form has
+# MORE flops than the head-wise one (768 vs 401 per row and channel) and the power-limited sustained loop is 0.3 % faster with
+# the tcgen05 cross-attention kernel there (390.5 vs 389.0 steps/s), so the default folds the 32x32 and 16x16 levels only.
+CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "640,1280").split(",") if v)
 
 
 class UNetOutput:
