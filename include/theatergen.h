@@ -110,6 +110,14 @@ int tg_cross_apply(const tg_half* P, int ldp, const tg_half* Vf, int B, int HW, 
  * reference runs everything on one stream.) */
 int tg_gemm_set_scratch_slot(int slot);
 
+/* Programmatic dependent launch (every kernel of the library is launched with programmatic stream serialisation: its
+ * prologue overlaps the previous kernel's tail) for the launches the calling host thread enqueues next: 0 = off, 1 = on,
+ * -1 = the process default (on; TG_PDL=0 turns it off).  A pre-launched dependent holds the SMs that the previous kernel's
+ * early-finishing CTAs free; while a second branch runs on another stream (the ControlNet encoder beside the UNet encoder)
+ * those SMs are better given to that branch, so the module-level path switches it off for the UNet encoder of a stage-2
+ * step.  (No reference counterpart.) */
+int tg_set_pdl(int mode);
+
 /* Measurement hook (no reference counterpart): with a non-NULL device buffer of >= 8*grid int64, every tg_gemm /
  * tg_conv3x3 CTA records {main-loop cycles, producer wait, MMA wait on data, MMA wait on accumulator, epilogue wait,
  * k-blocks, tiles} so a run can tell which role of the pipeline the others wait for.  NULL switches it off. */

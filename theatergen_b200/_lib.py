@@ -28,6 +28,7 @@ _SIGS = {
     "tg_conv3x3_s2": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp]),
     "tg_upsample2x_conv3x3": (ci, [vp, ci, ci, ci, ci, vp, ci, vp, vp, vp]),
     "tg_gemm_set_scratch_slot": (ci, [ci]),
+    "tg_set_pdl": (ci, [ci]),
     "tg_cross_scores": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp, vp, ci, vp]),
     "tg_cross_apply": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, vp]),
     "tg_gemm_set_stats": (ci, [vp, ci]),

@@ -100,6 +100,10 @@ int tg_groupnorm(const tg_half* x1, int C1, const tg_half* x2, int C2, int B, in
 }
 
 int tg_gemm_set_scratch_slot(int slot) { return tg::gemm_set_scratch_slot(slot); }
+int tg_set_pdl(int mode) {
+  tg::set_pdl(mode);
+  return 0;
+}
 
 int tg_attn_cross_set_impl(int mode) {
   TG_CHECK(mode >= -1 && mode <= 1, "tg_attn_cross_set_impl: %d (-1 auto, 0 mma.sync, 1 tcgen05)", mode);

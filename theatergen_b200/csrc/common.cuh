@@ -284,6 +284,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // host: kernel launch with programmatic stream serialization (PDL) and optional thread-block clusters
 // ----------------------------------------------------------------------------------------------
 bool pdl_enabled();  // TG_PDL=0 disables (A/B testing)
+void set_pdl(int mode);  // per host thread: -1 process default, 0 off, 1 on (tg_set_pdl)
 
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>

@@ -19,7 +19,12 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// per host thread: -1 = the process default (TG_PDL), 0 / 1 = off / on for the launches this thread enqueues next
+static thread_local int g_pdl_override = -1;
+void set_pdl(int mode) { g_pdl_override = mode < 0 ? -1 : (mode != 0); }
+
 bool pdl_enabled() {
+  if (g_pdl_override >= 0) return g_pdl_override != 0;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TG_PDL");

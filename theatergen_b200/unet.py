@@ -28,6 +28,7 @@ FOLD_FF2_PROJ_OUT = os.environ.get("TG_FOLD_FF2", "1") != "0"
 # (8x8: an image has fewer rows than a GEMM tile) always keeps the attention kernel.  At C = 320 (64x64) the folded form has
 # MORE flops than the head-wise one (768 vs 401 per row and channel) and the power-limited sustained loop is 0.3 % faster with
 # the tcgen05 cross-attention kernel there (390.5 vs 389.0 steps/s), so the default folds the 32x32 and 16x16 levels only.
+OVERLAP_PDL_DEFAULT = "00"
 CROSS_FOLD_C = tuple(int(v) for v in os.environ.get("TG_CROSS_FOLD", "640,1280").split(",") if v)
 
 
@@ -570,6 +571,7 @@ class TGUNet(_BlockNet):
                                         save_keys, cond_only, token_idx, capture_b0, controlnet, control, unique, n_text, n_ip)
         finally:
             self._stats_end()
+            _lib.lib().tg_set_pdl(-1)
 
     def _forward_blocks(self, sample, t_dev, temb_all, ctxkv, ip_scale, down_residuals, mid_residual, capture, save_keys,
                         cond_only, token_idx, capture_b0, controlnet, control, unique, n_text, n_ip):
@@ -593,12 +595,18 @@ class TGUNet(_BlockNet):
                 side = self._side_stream()
                 side.wait_stream(main)
                 _lib.check(_lib.lib().tg_gemm_set_scratch_slot(1), "tg_gemm_set_scratch_slot")  # own split-K workspace
+                # programmatic dependent launch while the two encoders share the GPU (include/theatergen.h tg_set_pdl): a
+                # pre-launched UNet kernel would sit on the SMs its predecessor's tail frees instead of leaving them to the
+                # ControlNet branch.  TG_OVERLAP_PDL = "<UNet><ControlNet>" (A/B), default "00" (measured 12.13 ms per co-batched step vs 12.22 for "11", 12.50 for "01", 12.30 for "10")
+                mode = os.environ.get("TG_OVERLAP_PDL", OVERLAP_PDL_DEFAULT)
                 try:
+                    _lib.lib().tg_set_pdl(int(mode[1]))
                     with torch.cuda.stream(side):
                         ctrl = controlnet.encode(sample[r0:r1], t_dev[r0:r1], control["ctx"], control["cond_emb"],
                                                  ctxkv=control.get("ctxkv"), share=control.get("share"))
                 finally:
                     _lib.check(_lib.lib().tg_gemm_set_scratch_slot(0), "tg_gemm_set_scratch_slot")
+                    _lib.lib().tg_set_pdl(int(mode[0]))
         if unique is not None:
             s0 = self._take(unique[0].shape[0], 320, H * W)
             x = _set(ops.conv_in_gemm(unique[0], w["conv_in.w"], w["conv_in.b"], stats=s0), s0)
@@ -615,6 +623,7 @@ class TGUNet(_BlockNet):
             x._gn = None  # rewritten in place: the producer's totals no longer describe it
         if ctrl is not None:  # after the mid block: the last skip tensor is also the mid block's input
             if side is not None:
+                _lib.lib().tg_set_pdl(-1)
                 torch.cuda.current_stream().wait_stream(side)
             controlnet.add_residuals_inplace(ctrl, skips, x, r0, r1, take=self._take)
         for i in range(4):
