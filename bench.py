@@ -612,6 +612,37 @@ def run_ours(args):
             "algorithmic_bytes": 2.0 * (40960 * 320 * 2 + 320 * 2880),
             "traffic": "see profiles/ (dram__bytes_read+write of the captured launches)"}
 
+    # second family by time: the 64x64 self-attention (N = 4096, d = 40, 8 heads, B = 10), timed alone.  Its bound is not the
+    # tensor pipe: one exponential per score, 16 MUFU.EX2 per clock and SM (tools/probes/xu_probe.cu), against 4 d = 160 flop
+    # per score -- at d = 40 the XU pipe saturates at 26 % tensor-pipe activity (profiles/r02_attention.md).
+    if rank == 0:
+        Ba, Na, da, ha = 10, 4096, 40, 8
+        qkv_a = torch.randn(Ba * Na, 3 * ha * da, device=dev).half()
+        oa = torch.empty(Ba * Na, ha * da, device=dev, dtype=torch.float16)
+        Ca = ha * da
+
+        def _attn():
+            ops.attention_tc(qkv_a[:, :Ca], qkv_a[:, Ca:2 * Ca], qkv_a[:, 2 * Ca:], Ba, ha, da, out=oa, packed=True)
+        for _ in range(3):
+            _attn()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s_.record()
+        for _ in range(10):
+            _attn()
+        e_.record()
+        torch.cuda.synchronize()
+        us = s_.elapsed_time(e_) / 10 * 1e3
+        exps = float(Ba) * ha * Na * Na
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        xu_peak = sm_count * 16 * 1.965e9 / 1e12  # Texp/s at the maximum SM clock
+        roof["attention_64x64"] = {
+            "what": "attn_tc_kernel<1>: self-attention N=4096 d=40 heads=8 B=10 (packed heads), timed alone, 10 launches",
+            "us": round(us, 1), "bound": "xu (MUFU.EX2, 16 per clock and SM)", "achieved": round(exps / us / 1e6, 3),
+            "peak": round(xu_peak, 3), "unit": "Texp/s", "frac": round(exps / us / 1e6 / xu_peak, 4),
+            "tensor_tflops": round(4.0 * exps * da / us / 1e6, 1)}
+        del qkv_a, oa
+
     # Reported beside the main number, never inside it: one iteration of latent_backward_guidance --
     # conditional forward to the last guidance key, energy, d(energy)/d(latents) through the UNet, latent update.  The
     # reference has no caller for it; this is the cost a caller would pay per iteration.
