@@ -36,3 +36,23 @@ def test_no_compute_without_gpu_is_an_error_not_a_fallback():
     assert rc != 0 and len(l.tg_last_error()) > 0   # fails loudly: no device, no CPU path
     from theatergen_b200.unet import TGUNet  # noqa: F401
     assert "oracle" not in open(os.path.join(ROOT, "theatergen_b200", "unet.py")).read().replace("oracle/unet.py", "")
+
+
+def test_plain_c_host_loads_the_library(tmp_path):
+    """A C99 host (tests/c_host/abi_check.c, no CUDA headers, no Python): include/theatergen.h compiles as C with -pedantic, the
+    library loads with dlopen, every declared entry point resolves and a call with null operands is refused with a message."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    import __graft_entry__
+    __graft_entry__.build()
+    from theatergen_b200 import _lib
+    exe = str(tmp_path / "abi_check")
+    src = os.path.join(ROOT, "tests", "c_host", "abi_check.c")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), src,
+                        "-ldl", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe, _lib.LIB_PATH, *_declared()], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr)
