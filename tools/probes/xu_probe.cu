@@ -72,6 +72,14 @@ __global__ void __launch_bounds__(256, 1) probe(int iters, float seed, long long
         asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(a), "l"(b));
         asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(x[i]), "=f"(x[i + 1]) : "l"(v));
       }
+    } else if (MODE == 9) {  // 64 exponentials as 32 ex2.approx.f16x2 (SASS: 2 x MUFU.EX2.F16 + PRMT each) on packed halves
+      uint32_t* xh = reinterpret_cast<uint32_t*>(x);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        uint32_t y;
+        asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(xh[i]));
+        xh[i] = y ^ 0x80008000u;  // keep the chain dependent and the values bounded (sign flip)
+      }
     } else if (MODE == 8) {  // 128 FFMA
 #pragma unroll
       for (int i = 0; i < 64; ++i) { x[i] = fmaf(x[i], 1.0001f, 0.001f); x[i] = fmaf(x[i], 1.0001f, 0.001f); }
@@ -110,5 +118,6 @@ int main() {
   run<6>("32 MUFU.EX2 + 32 polynomial (+64 FADD)", d_out, d_sink);
   run<7>("64 FFMA2 (= 128 fp32 FMA) + pack/unpack movs", d_out, d_sink);
   run<8>("128 FFMA", d_out, d_sink);
+  run<9>("32 ex2.approx.f16x2 (= 64 MUFU.EX2.F16, +32 LOP)", d_out, d_sink);
   return 0;
 }
