@@ -262,6 +262,32 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return 0.5f * x * (1.f + copysignf(e, x));
 }
 
+// The same polynomial on W values at once, Horner step by Horner step: W independent dependency chains side by side, so the
+// 4-cycle FMA latency of one chain is covered by the others even when the register allocator keeps few values in flight
+// (a GEGLU epilogue evaluated element by element ran ~70 cycles per element: one dependent chain at a time).
+template <int W>
+__device__ __forceinline__ void gelu_erf_fast_n(const float (&x)[W], float (&y)[W]) {
+  float z[W], t[W], p[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    z[j] = fminf(fabsf(x[j]) * 0.70710678118654752f, 3.2f);
+    t[j] = z[j] * z[j];
+    p[j] = 3.4405886140120856e-08f;
+  }
+  const float c[8] = {-1.7486363503849134e-06f, 3.880867370753549e-05f, -0.0005002432153560221f, 0.004227499943226576f,
+                      -0.025213463231921196f, 0.11144663393497467f, -0.3756941556930542f, 1.1283652782440186f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) p[j] = fmaf(p[j], t[j], c[k]);
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const float e = fminf(p[j] * z[j], 1.f);
+    y[j] = 0.5f * x[j] * (1.f + copysignf(e, x[j]));
+  }
+}
+
 // 3-input maximum (PTX ISA 8.6, sm_100: one FMNMX3 instead of two FMNMX)
 __device__ __forceinline__ float fmax3f(float a, float b, float c) {
   float d;

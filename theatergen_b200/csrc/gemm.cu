@@ -759,18 +759,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           const uint4* bpa = reinterpret_cast<const uint4*>(g.bias + n0 + c);
           const uint4* bpg = bpa + 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 4; ++i) {  // eight outputs at a time, their GELU polynomials evaluated side by side
             const uint4 ba = __ldg(bpa + i), bg = __ldg(bpg + i);
             const __half2* ha = reinterpret_cast<const __half2*>(&ba);
             const __half2* hg = reinterpret_cast<const __half2*>(&bg);
+            float gate[8], ge[8];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-              const float2 fa = __half22float2(ha[jj]), fg = __half22float2(hg[jj]);
+              const float2 fg = __half22float2(hg[jj]);
+              gate[2 * jj] = __uint_as_float(rg[i * 8 + 2 * jj]) + fg.x;
+              gate[2 * jj + 1] = __uint_as_float(rg[i * 8 + 2 * jj + 1]) + fg.y;
+            }
+            gelu_erf_fast_n<8>(gate, ge);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float2 fa = __half22float2(ha[jj]);
               const int ee = i * 8 + jj * 2;
-              const float a0 = __uint_as_float(ra[ee]) + fa.x, a1 = __uint_as_float(ra[ee + 1]) + fa.y;
-              const float g0 = __uint_as_float(rg[ee]) + fg.x, g1 = __uint_as_float(rg[ee + 1]) + fg.y;
-              v[ee] = a0 * gelu_erf_fast(g0);
-              v[ee + 1] = a1 * gelu_erf_fast(g1);
+              v[ee] = (__uint_as_float(ra[ee]) + fa.x) * ge[2 * jj];
+              v[ee + 1] = (__uint_as_float(ra[ee + 1]) + fa.y) * ge[2 * jj + 1];
             }
           }
         }
